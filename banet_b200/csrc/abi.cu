@@ -1,0 +1,202 @@
+// extern "C" entry points of libbanet_sm100.so (see include/banet_abi.h) + the LM driver loop.
+#include "common.cuh"
+#include "lm_build.h"
+#include <string.h>
+
+namespace banet {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int num_sms()
+{
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return kMaxSMs; }
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { cudaGetLastError(); return kMaxSMs; }
+    return n;
+}
+
+static int check_level(const banet_level_t* lv, const char* who)
+{
+    BANET_REQUIRE(lv, BANET_ERR_BAD_ARG, "%s: null level", who);
+    BANET_REQUIRE(lv->nb > 0 && lv->N > 0 && lv->C > 0 && lv->K >= 0 && lv->h >= 2 && lv->w >= 2, BANET_ERR_BAD_ARG,
+                  "%s: bad shape nb=%d N=%d C=%d K=%d h=%d w=%d", who, lv->nb, lv->N, lv->C, lv->K, lv->h, lv->w);
+    BANET_REQUIRE(lv->conv2_channels == 3 * lv->C || lv->conv2_channels == lv->C, BANET_ERR_BAD_ARG,
+                  "%s: conv2_channels=%d must be 3*C (reference layout) or C (F2 only)", who, lv->conv2_channels);
+    BANET_REQUIRE(lv->conv1 && lv->conv2 && lv->intr && lv->p && lv->D, BANET_ERR_BAD_ARG, "%s: null tensor", who);
+    BANET_REQUIRE(lv->K == 0 || lv->B, BANET_ERR_BAD_ARG, "%s: K=%d but B is null", who, lv->K);
+    BANET_REQUIRE((long long)lv->h * lv->w * lv->conv2_channels < (1LL << 40), BANET_ERR_BAD_ARG, "%s: map too large", who);
+    return BANET_OK;
+}
+
+}  // namespace banet
+
+using namespace banet;
+
+extern "C" int banet_abi_version(void) { return BANET_ABI_VERSION; }
+extern "C" const char* banet_last_error(void) { return g_err; }
+extern "C" int banet_num_sms(void) { return num_sms(); }
+
+extern "C" int banet_device_check(void)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); set_error("no CUDA device: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
+    int major = 0, minor = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    BANET_REQUIRE(major == 10, BANET_ERR_UNSUPPORTED, "device compute capability %d.%d; this library is built for sm_100a only", major, minor);
+    return BANET_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+extern "C" size_t banet_lm_build_workspace_bytes(const banet_level_t* lv, int precision)
+{
+    (void)precision;
+    if (!lv) return 0;
+    BuildPlan plan;
+    if (build_plan(lv, num_sms(), &plan) != BANET_OK) return 0;
+    return plan.ws_bytes;
+}
+
+extern "C" int banet_lm_build(const banet_level_t* lv, const float* R, const float* T, const float* W, int precision,
+                              float* H, float* g, float* rbar_sum, float* nvalid, void* ws, size_t ws_bytes, banet_stream_t stream)
+{
+    int rc = check_level(lv, "lm_build");
+    if (rc) return rc;
+    BANET_REQUIRE(R && T && H && g && rbar_sum && nvalid, BANET_ERR_BAD_ARG, "lm_build: null pointer");
+    BANET_REQUIRE(lv->K == 0 || W, BANET_ERR_BAD_ARG, "lm_build: K=%d but W is null", lv->K);
+    BANET_REQUIRE(precision == BANET_PREC_FP32_SIMT, BANET_ERR_UNSUPPORTED, "lm_build: precision mode %d not available in this build", precision);
+    BuildPlan plan;
+    rc = build_plan(lv, num_sms(), &plan);
+    if (rc) return rc;
+    BANET_REQUIRE(ws && ws_bytes >= plan.ws_bytes, BANET_ERR_WORKSPACE, "lm_build: workspace %zu < %zu bytes", ws_bytes, plan.ws_bytes);
+    return lm_build_simt(lv, plan, R, T, W, H, g, rbar_sum, nvalid, ws, (cudaStream_t)stream);
+}
+
+extern "C" size_t banet_mlp_param_count(int C) { return (size_t)20 * C * C + (size_t)10 * C + 1; }
+
+extern "C" int banet_lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp_weights, float base,
+                               float* lambda_out, banet_stream_t stream)
+{
+    BANET_REQUIRE(rbar_sum && mlp_weights && lambda_out && nb > 0 && N > 0 && C > 0, BANET_ERR_BAD_ARG, "lm_lambda: bad argument");
+    return lm_lambda(rbar_sum, nb, N, C, mlp_weights, base, lambda_out, (cudaStream_t)stream);
+}
+
+extern "C" size_t banet_lm_solve_workspace_bytes(int nb, int K)
+{
+    if (nb <= 0 || K < 0) return 0;
+    return align_up((size_t)nb * (6 + K) * sizeof(float), 256);
+}
+
+extern "C" int banet_lm_solve_update(const float* H, const float* g, const float* lambda, int nb, int K,
+                                     const banet_solve_opts_t* opts, const float* R, const float* T, const float* W,
+                                     float* R_out, float* T_out, float* W_out, float* delta, int32_t* status,
+                                     void* ws, size_t ws_bytes, banet_stream_t stream)
+{
+    BANET_REQUIRE(H && g && lambda && opts && R && T && R_out && T_out && status, BANET_ERR_BAD_ARG, "lm_solve_update: null pointer");
+    BANET_REQUIRE(nb > 0 && K >= 0, BANET_ERR_BAD_ARG, "lm_solve_update: bad shape nb=%d K=%d", nb, K);
+    BANET_REQUIRE(K == 0 || (W && W_out), BANET_ERR_BAD_ARG, "lm_solve_update: K=%d but W is null", K);
+    if (!delta) {
+        BANET_REQUIRE(ws && ws_bytes >= banet_lm_solve_workspace_bytes(nb, K), BANET_ERR_WORKSPACE,
+                      "lm_solve_update: delta is null and workspace %zu < %zu bytes", ws_bytes, banet_lm_solve_workspace_bytes(nb, K));
+        delta = reinterpret_cast<float*>(ws);
+    }
+    return lm_solve_update(H, g, lambda, nb, K, *opts, R, T, W, R_out, T_out, W_out, delta, status, 0, (cudaStream_t)stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// whole solve
+namespace {
+struct RunCarve { size_t build, H, g, rbar, nvalid, lambda, delta, total; };
+int carve(const banet_level_t* levels, int nlevels, int precision, RunCarve* c)
+{
+    (void)precision;
+    size_t build = 0; int maxC = 0;
+    const int nb = levels[0].nb, K = levels[0].K, P = 6 + K;
+    for (int l = 0; l < nlevels; ++l) {
+        BuildPlan plan;
+        int rc = build_plan(&levels[l], num_sms(), &plan);
+        if (rc) return rc;
+        if (plan.ws_bytes > build) build = plan.ws_bytes;
+        if (levels[l].C > maxC) maxC = levels[l].C;
+    }
+    size_t off = 0;
+    c->build = off;  off += align_up(build, 256);
+    c->H = off;      off += align_up((size_t)nb * P * P * 4, 256);
+    c->g = off;      off += align_up((size_t)nb * P * 4, 256);
+    c->rbar = off;   off += align_up((size_t)nb * maxC * 4, 256);
+    c->nvalid = off; off += align_up((size_t)nb * 4, 256);
+    c->lambda = off; off += align_up((size_t)nb * 4, 256);
+    c->delta = off;  off += align_up((size_t)nb * P * 4, 256);
+    c->total = off;
+    return BANET_OK;
+}
+__global__ void fill_kernel(float* p, int n, float v) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
+__global__ void zero_status_kernel(int32_t* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0; }
+}  // namespace
+
+extern "C" size_t banet_lm_run_workspace_bytes(const banet_level_t* levels, int nlevels, int precision)
+{
+    if (!levels || nlevels <= 0) return 0;
+    RunCarve c;
+    if (carve(levels, nlevels, precision, &c) != BANET_OK) return 0;
+    return c.total;
+}
+
+extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_per_level,
+                            const float* const* mlp_weights, float l2_regularizer_base, float lambda_fixed,
+                            const banet_solve_opts_t* opts, int precision,
+                            float* R, float* T, float* W, int32_t* status, void* ws, size_t ws_bytes, banet_stream_t stream)
+{
+    BANET_REQUIRE(levels && nlevels > 0 && iters_per_level > 0 && opts && R && T && status, BANET_ERR_BAD_ARG, "lm_run: bad argument");
+    BANET_REQUIRE(precision == BANET_PREC_FP32_SIMT, BANET_ERR_UNSUPPORTED, "lm_run: precision mode %d not available in this build", precision);
+    const int nb = levels[0].nb, K = levels[0].K;
+    for (int l = 0; l < nlevels; ++l) {
+        int rc = check_level(&levels[l], "lm_run");
+        if (rc) return rc;
+        BANET_REQUIRE(levels[l].nb == nb && levels[l].K == K, BANET_ERR_BAD_ARG, "lm_run: nb/K must agree across levels");
+        BANET_REQUIRE((mlp_weights && mlp_weights[l]) || lambda_fixed >= 0.f, BANET_ERR_BAD_ARG,
+                      "lm_run: level %d has no lambda-MLP weights and lambda_fixed < 0", l);
+    }
+    BANET_REQUIRE(K == 0 || W, BANET_ERR_BAD_ARG, "lm_run: K=%d but W is null", K);
+    RunCarve c;
+    int rc = carve(levels, nlevels, precision, &c);
+    if (rc) return rc;
+    BANET_REQUIRE(ws && ws_bytes >= c.total, BANET_ERR_WORKSPACE, "lm_run: workspace %zu < %zu bytes", ws_bytes, c.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(ws);
+    float* H = reinterpret_cast<float*>(base + c.H);
+    float* g = reinterpret_cast<float*>(base + c.g);
+    float* rbar = reinterpret_cast<float*>(base + c.rbar);
+    float* nvalid = reinterpret_cast<float*>(base + c.nvalid);
+    float* lam = reinterpret_cast<float*>(base + c.lambda);
+    float* delta = reinterpret_cast<float*>(base + c.delta);
+    zero_status_kernel<<<(nb + 255) / 256, 256, 0, st>>>(status, nb);
+    for (int l = 0; l < nlevels; ++l) {
+        const banet_level_t* lv = &levels[l];
+        BuildPlan plan;
+        rc = build_plan(lv, num_sms(), &plan);
+        if (rc) return rc;
+        const bool use_mlp = mlp_weights && mlp_weights[l] && lambda_fixed < 0.f;
+        if (!use_mlp) fill_kernel<<<(nb + 255) / 256, 256, 0, st>>>(lam, nb, lambda_fixed);
+        for (int it = 0; it < iters_per_level; ++it) {
+            rc = lm_build_simt(lv, plan, R, T, W, H, g, rbar, nvalid, base + c.build, st);
+            if (rc) return rc;
+            if (use_mlp) {
+                rc = lm_lambda(rbar, nb, lv->N, lv->C, mlp_weights[l], l2_regularizer_base, lam, st);
+                if (rc) return rc;
+            }
+            rc = lm_solve_update(H, g, lam, nb, K, *opts, R, T, W, R, T, W, delta, status, 1, st);
+            if (rc) return rc;
+        }
+    }
+    BANET_CUDA_LAUNCH_CHECK("lm_run");
+    return BANET_OK;
+}

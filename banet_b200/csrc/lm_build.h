@@ -1,0 +1,34 @@
+// Internal interfaces between the translation units of libbanet_sm100.so.
+#pragma once
+#include "common.cuh"
+
+namespace banet {
+
+struct BuildParams {
+    int nb, N, C, K, h, w, c2;
+    const float *conv1, *conv2, *intr, *p, *D, *B, *R, *T, *W;
+    float* partials;
+    int slot_floats, max_span, tiles_per_pair;
+    long long total_tiles;
+};
+
+struct BuildPlan {
+    int KP, grid, max_span, slot_floats, tiles_per_pair;
+    long long total_tiles;
+    size_t ws_bytes;
+};
+
+int num_sms();
+
+// fp32 SIMT path (lm_build.cu)
+int build_plan(const banet_level_t* lv, int num_sms, BuildPlan* plan);
+int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R, const float* T, const float* W,
+                  float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st);
+
+// lambda MLP / solve / update (lm_solve.cu)
+int lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp, float base, float* lambda_out, cudaStream_t st);
+int lm_solve_update(const float* H, const float* g, const float* lambda, int nb, int K, const banet_solve_opts_t& opts,
+                    const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+                    float* delta, int32_t* status, int status_accumulate, cudaStream_t st);
+
+}  // namespace banet

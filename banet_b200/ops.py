@@ -1,0 +1,257 @@
+"""Thin torch-facing wrappers over the C-ABI (include/banet_abi.h).  torch is plumbing only: it owns
+device memory and streams; all arithmetic happens in libbanet_sm100.so.  No fallbacks: CPU tensors or a
+missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BanetLevel, BanetSolveOpts, check, load
+
+Tensor = torch.Tensor
+
+
+def _chk(t: Tensor, name: str, shape: Optional[Tuple[int, ...]] = None) -> Tensor:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.BanetError(f"{name}: expected a CUDA tensor (banet_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise _lib.BanetError(f"{name}: expected float32, got {t.dtype}")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise _lib.BanetError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+    return t.contiguous()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _ws(nbytes: int, device) -> Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ op level
+class _EquationConstruction(torch.autograd.Function):
+    """Drop-in for the reference TF op `equation_construction` and its registered gradient
+    (reference bundlenet.py:76-82; utils.cu:150-171, 420-428)."""
+
+    @staticmethod
+    def forward(ctx, jacobian, gradient, difference, exact_sym):
+        lib = load()
+        J = _chk(jacobian, "jacobian"); nb, N, two, P = J.shape
+        Cc = gradient.shape[2]
+        G = _chk(gradient, "gradient", (nb, N, Cc, 2)); d = _chk(difference, "difference", (nb, N, Cc, 1))
+        if two != 2:
+            raise _lib.BanetError("jacobian must be [nb,N,2,P]")
+        AtA = torch.empty(nb, P, P, device=J.device, dtype=torch.float32)
+        Atb = torch.empty(nb, P, 1, device=J.device, dtype=torch.float32)
+        nbytes = lib.banet_eqc_workspace_bytes(nb, N, Cc, P)
+        ws = _ws(nbytes, J.device)
+        check(lib.banet_eqc_fwd(J.data_ptr(), G.data_ptr(), d.data_ptr(), nb, N, Cc, P, AtA.data_ptr(), Atb.data_ptr(),
+                                ws.data_ptr(), ws.numel(), _stream()), "banet_eqc_fwd")
+        ctx.save_for_backward(J, G, d)
+        ctx.exact_sym = bool(exact_sym)
+        return AtA, Atb
+
+    @staticmethod
+    def backward(ctx, gAtA, gAtb):
+        lib = load()
+        J, G, d = ctx.saved_tensors
+        nb, N, _, P = J.shape
+        Cc = G.shape[2]
+        gA = _chk(gAtA, "left_grad", (nb, P, P)); gb = _chk(gAtb, "right_grad", (nb, P, 1))
+        dJ = torch.empty_like(J); dG = torch.empty_like(G); dd = torch.empty_like(d)
+        check(lib.banet_eqc_bwd(J.data_ptr(), G.data_ptr(), d.data_ptr(), gA.data_ptr(), gb.data_ptr(), nb, N, Cc, P,
+                                1 if ctx.exact_sym else 0, dJ.data_ptr(), dG.data_ptr(), dd.data_ptr(), _stream()),
+              "banet_eqc_bwd")
+        return dJ, dG, dd, None
+
+
+def equation_construction(jacobian: Tensor, gradient: Tensor, difference: Tensor, exact_sym: bool = False):
+    """AtA, Atb = equation_construction(jacobian[nb,N,2,P], gradient[nb,N,C,2], difference[nb,N,C,1]).
+    Backward = the reference's `equation_construction_grad` (2*A*Ghat form) unless exact_sym."""
+    return _EquationConstruction.apply(jacobian, gradient, difference, exact_sym)
+
+
+def equation_construction_grad(jacobian, gradient, difference, left_grad, right_grad, exact_sym: bool = False):
+    """Direct call of the gradient op (reference utils.cu:420-428)."""
+    lib = load()
+    J = _chk(jacobian, "jacobian"); nb, N, _, P = J.shape
+    Cc = gradient.shape[2]
+    G = _chk(gradient, "gradient", (nb, N, Cc, 2)); d = _chk(difference, "difference", (nb, N, Cc, 1))
+    gA = _chk(left_grad, "left_grad", (nb, P, P)); gb = _chk(right_grad, "right_grad", (nb, P, 1))
+    dJ = torch.empty_like(J); dG = torch.empty_like(G); dd = torch.empty_like(d)
+    check(lib.banet_eqc_bwd(J.data_ptr(), G.data_ptr(), d.data_ptr(), gA.data_ptr(), gb.data_ptr(), nb, N, Cc, P,
+                            1 if exact_sym else 0, dJ.data_ptr(), dG.data_ptr(), dd.data_ptr(), _stream()), "banet_eqc_bwd")
+    return dJ, dG, dd
+
+
+# ------------------------------------------------------------------------------------------ pre-steps
+def compute_coordinates(points: Tensor, intr: Tensor, normalize: bool = True) -> Tensor:
+    lib = load()
+    pts = _chk(points, "points"); nb, N, _ = pts.shape
+    it = _chk(intr, "intr", (nb, 4))
+    p = torch.empty(nb, 3, N, device=pts.device, dtype=torch.float32)
+    check(lib.banet_compute_coordinates(pts.data_ptr(), it.data_ptr(), nb, N, int(normalize), p.data_ptr(), _stream()),
+          "banet_compute_coordinates")
+    return p
+
+
+def grad_fixed_concat(F: Tensor, swap_halves: bool = False) -> Tensor:
+    lib = load()
+    f = _chk(F, "F"); nb, h, w, Cc = f.shape
+    out = torch.empty(nb, h, w, 3 * Cc, device=f.device, dtype=torch.float32)
+    check(lib.banet_grad_fixed_concat(f.data_ptr(), nb, h, w, Cc, int(swap_halves), out.data_ptr(), _stream()),
+          "banet_grad_fixed_concat")
+    return out
+
+
+def resample(data: Tensor, xy: Tensor, coord_scale: float = 1.0) -> Tensor:
+    lib = load()
+    dt = _chk(data, "data"); nb, h, w, Cc = dt.shape
+    pts = _chk(xy, "xy"); N = pts.shape[1]
+    out = torch.empty(nb, N, Cc, device=dt.device, dtype=torch.float32)
+    check(lib.banet_resample(dt.data_ptr(), pts.data_ptr(), float(coord_scale), nb, h, w, Cc, N, out.data_ptr(), _stream()),
+          "banet_resample")
+    return out
+
+
+def depth_compose(init_depth: Tensor, basis: Tensor, W: Tensor) -> Tensor:
+    """init_depth [nb,M], basis [nb,M,K], W [nb,K,1] -> [nb,M]   (reference bundlenet.py:397)."""
+    lib = load()
+    bs = _chk(basis, "basis"); nb, M, K = bs.shape
+    d0 = _chk(init_depth, "init_depth", (nb, M)); Wt = _chk(W, "W", (nb, K, 1))
+    out = torch.empty(nb, M, device=bs.device, dtype=torch.float32)
+    check(lib.banet_depth_compose(d0.data_ptr(), bs.data_ptr(), Wt.data_ptr(), nb, M, K, out.data_ptr(), _stream()),
+          "banet_depth_compose")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ layer level
+@dataclass
+class Level:
+    """One pyramid level in the reference's tensor layouts (see banet_level in include/banet_abi.h)."""
+    conv1: Tensor             # [nb,N,C]
+    conv2: Tensor             # [nb,h,w,3C]  ([nb,h,w,C]: F2 only, gradients derived on the fly)
+    intr: Tensor              # [nb,4]
+    p: Tensor                 # [nb,3,N]
+    D: Tensor                 # [nb,N,1]
+    B: Optional[Tensor]       # [nb,N,K] or None
+
+    def as_struct(self) -> Tuple[BanetLevel, list]:
+        conv1 = _chk(self.conv1, "conv1"); nb, N, Cc = conv1.shape
+        conv2 = _chk(self.conv2, "conv2"); _, h, w, c2 = conv2.shape
+        intr = _chk(self.intr, "intr", (nb, 4)); p = _chk(self.p, "p", (nb, 3, N)); D = _chk(self.D, "D", (nb, N, 1))
+        B = None if self.B is None else _chk(self.B, "B")
+        K = 0 if B is None else B.shape[2]
+        if B is not None and tuple(B.shape[:2]) != (nb, N):
+            raise _lib.BanetError(f"B: expected [nb,N,K]=[{nb},{N},K], got {tuple(B.shape)}")
+        if conv2.shape[0] != nb:
+            raise _lib.BanetError("conv2 batch mismatch")
+        keep = [conv1, conv2, intr, p, D, B]
+        return BanetLevel(nb, N, Cc, K, h, w, c2, conv1.data_ptr(), conv2.data_ptr(), intr.data_ptr(), p.data_ptr(),
+                          D.data_ptr(), _ptr(B)), keep
+
+
+def lm_build(level: Level, R: Tensor, T: Tensor, W: Optional[Tensor], precision: int = _lib.PREC_FP32_SIMT):
+    """H [nb,P,P], g [nb,P], rbar_sum [nb,C], nvalid [nb] of one iteration at the current (R,T,W)."""
+    lib = load()
+    st, keep = level.as_struct()
+    nb, K, Cc = st.nb, st.K, st.C
+    P = 6 + K
+    R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1))
+    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1))
+    dev = R.device
+    H = torch.empty(nb, P, P, device=dev, dtype=torch.float32); g = torch.empty(nb, P, device=dev, dtype=torch.float32)
+    rbar = torch.empty(nb, Cc, device=dev, dtype=torch.float32); nvalid = torch.empty(nb, device=dev, dtype=torch.float32)
+    ws = _ws(lib.banet_lm_build_workspace_bytes(C.byref(st), precision), dev)
+    check(lib.banet_lm_build(C.byref(st), R.data_ptr(), T.data_ptr(), _ptr(Wt), precision, H.data_ptr(), g.data_ptr(),
+                             rbar.data_ptr(), nvalid.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_build")
+    return H, g, rbar, nvalid
+
+
+def pack_mlp(params: Sequence[Tuple[Tensor, Tensor]]) -> Tensor:
+    """[(W1[cin,cout], b1[cout]), ...x5] -> packed fp32 buffer expected by banet_lm_lambda."""
+    return torch.cat([t.reshape(-1).to(torch.float32) for wb in params for t in wb]).contiguous()
+
+
+def lm_lambda(rbar_sum: Tensor, N: int, mlp_packed: Tensor, base: float) -> Tensor:
+    lib = load()
+    rb = _chk(rbar_sum, "rbar_sum"); nb, Cc = rb.shape
+    mp = _chk(mlp_packed, "mlp_packed")
+    if mp.numel() != lib.banet_mlp_param_count(Cc):
+        raise _lib.BanetError(f"mlp_packed has {mp.numel()} params, expected {lib.banet_mlp_param_count(Cc)} for C={Cc}")
+    lam = torch.empty(nb, device=rb.device, dtype=torch.float32)
+    check(lib.banet_lm_lambda(rb.data_ptr(), nb, int(N), Cc, mp.data_ptr(), float(base), lam.data_ptr(), _stream()), "banet_lm_lambda")
+    return lam
+
+
+def lm_solve_update(H: Tensor, g: Tensor, lam: Tensor, R: Tensor, T: Tensor, W: Optional[Tensor],
+                    damping_eps: float = 1e-5, undamped_last: bool = True, vmatrix_batch_scramble: bool = False):
+    """-> R', T', W', delta [nb,P], status [nb] (int32)."""
+    lib = load()
+    Hc = _chk(H, "H"); nb, P, _ = Hc.shape
+    K = P - 6
+    gc = _chk(g.reshape(nb, P), "g", (nb, P)); lc = _chk(lam.reshape(nb), "lambda", (nb,))
+    R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1))
+    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1))
+    dev = Hc.device
+    Ro = torch.empty_like(R); To = torch.empty_like(T); Wo = None if K == 0 else torch.empty_like(Wt)
+    delta = torch.empty(nb, P, device=dev, dtype=torch.float32)
+    status = torch.empty(nb, device=dev, dtype=torch.int32)
+    opts = BanetSolveOpts(float(damping_eps), int(undamped_last), int(vmatrix_batch_scramble))
+    check(lib.banet_lm_solve_update(Hc.data_ptr(), gc.data_ptr(), lc.data_ptr(), nb, K, C.byref(opts), R.data_ptr(), T.data_ptr(),
+                                    _ptr(Wt), Ro.data_ptr(), To.data_ptr(), _ptr(Wo), delta.data_ptr(), status.data_ptr(),
+                                    None, 0, _stream()), "banet_lm_solve_update")
+    return Ro, To, Wo, delta, status
+
+
+def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
+           mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: float = 1000.0,
+           lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,
+           vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_FP32_SIMT, workspace: Optional[Tensor] = None):
+    """Whole coarse-to-fine solve on the device (banet_lm_run).  Returns new (R,T,W,status); inputs are not modified."""
+    lib = load()
+    structs, keep = [], []
+    for lv in levels:
+        s, k = lv.as_struct(); structs.append(s); keep.append(k)
+    arr = (BanetLevel * len(structs))(*structs)
+    nb, K = structs[0].nb, structs[0].K
+    R = _chk(R, "R", (nb, 3, 3)).clone(); T = _chk(T, "T", (nb, 3, 1)).clone()
+    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1)).clone()
+    if undamped_last is None:
+        undamped_last = K > 0
+    mlp_ptrs = (C.c_void_p * len(structs))()
+    have = False
+    for i in range(len(structs)):
+        m = None if mlp_packed is None else mlp_packed[i]
+        if m is not None:
+            m = _chk(m, "mlp_packed"); keep.append(m); have = True
+            if m.numel() != lib.banet_mlp_param_count(structs[i].C):
+                raise _lib.BanetError("mlp_packed size mismatch")
+        mlp_ptrs[i] = None if m is None else m.data_ptr()
+    opts = BanetSolveOpts(float(damping_eps), int(undamped_last), int(vmatrix_batch_scramble))
+    nbytes = lib.banet_lm_run_workspace_bytes(arr, len(structs), precision)
+    if nbytes == 0:
+        check(-4, "banet_lm_run_workspace_bytes")
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else _ws(nbytes, R.device)
+    status = torch.empty(nb, device=R.device, dtype=torch.int32)
+    check(lib.banet_lm_run(arr, len(structs), int(iters_per_level), mlp_ptrs if have else None, float(l2_regularizer_base),
+                           float(lambda_fixed), C.byref(opts), precision, R.data_ptr(), T.data_ptr(), _ptr(Wt),
+                           status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_run")
+    return R, T, Wt, status
+
+
+def lm_run_workspace_bytes(levels: Sequence[Level], precision: int = _lib.PREC_FP32_SIMT) -> int:
+    lib = load()
+    structs = [lv.as_struct()[0] for lv in levels]
+    arr = (BanetLevel * len(structs))(*structs)
+    return int(lib.banet_lm_run_workspace_bytes(arr, len(structs), precision))

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — LM iterations/sec of the BA layer's inner loop (BASELINE.json metric) on N B200s.
+
+A "step" is one whole coarse-to-fine solve of BASELINE config 2 on every rank's shard:
+nb=32 frame-pairs per GPU, dense levels 80x60 -> 640x480 (ΣN = 408 000 points/pair), C=128 feature
+channels, K=128 depth bases, 5 LM iterations per level (20 iterations), lambda-MLP in the loop.
+Frame-pairs are independent, so ranks hold disjoint shards (weak scaling) and the only collective is
+one all-gather of the solved (R,T,W) at the end of each step.
+
+value      pair-iterations/s  = (total pairs) * 20 / t_step      inputs resident in HBM
+e2e        the same through the public API with HOST buffers: pinned host -> device copies of every
+           level tensor + the solve + device -> host read of (R,T,W), all inside the timed region
+roofline   dominant kernel lm_build_kernel: algorithmic bytes 4*N*(2C+K+4)+4*(P^2+P+C) per pair
+            / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference
+           the reference cannot execute here (TF-1.x / python2 / TF headers absent), so the reference arm is
+           the oracle's reference-faithful materialised restatement (J,G,d tensors + batched matmul chain +
+           LU solve, torch-CPU fp32, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "LM iters/sec (frame-pair LM iterations, 640x480x4-scale, K=128)"
+UNIT = "pair-iters/s"
+LEVEL_IDS = (0, 1, 2, 3)
+H_FULL, W_FULL = 480, 640
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nb", type=int, default=32, help="frame-pairs per GPU")
+    ap.add_argument("--channels", type=int, default=128)
+    ap.add_argument("--bases", type=int, default=128)
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def algorithmic_bytes_per_pair_iter(N, C, K):
+    """dense level, conv1 + each F2 texel once + B + ray/depth + outputs."""
+    P = 6 + K
+    return 4 * N * (2 * C + K + 4) + 4 * (P * P + P + C)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index; self.lines = []; self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_sample(C, K, reps, seed=1234):
+    """Times the oracle's materialised BundleIteration (reference-faithful: J,G,d tensors, matmul chain, LU) on ONE
+    pair at the 160x120 level (N = 19 200) in fp32 with all host threads; returns seconds per pair-iteration there."""
+    from oracle import ba_oracle as O
+    from banet_b200 import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sc = synth.make_scene(nb=1, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=(1,), seed=seed, dtype=torch.float32, device="cpu")
+    lv = sc.levels[0]
+    fx, fy, ox, oy = lv.intr_tiled()
+    mlp = O.init_lambda_mlp(C, dtype=torch.float32)
+    times = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            O.bundle_iteration(lv.conv1, lv.conv2, fx, fy, ox, oy, lv.p, lv.D, lv.B, sc.R0, sc.T0, sc.W0, mlp)
+            times.append(time.perf_counter() - t0)
+    return times[1:], lv.N, cores        # first call is a warm-up
+
+
+def pixels_per_pair_iter():
+    """A pair-iteration of the 4-level workload touches ΣN/4 points on average."""
+    tot = sum((H_FULL // 2 ** (3 - l)) * (W_FULL // 2 ** (3 - l)) for l in LEVEL_IDS)
+    return tot / len(LEVEL_IDS)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, args.steps)
+    times, n_sample, cores = cpu_reference_sample(args.channels, args.bases, reps)
+    t = sorted(times)[len(times) // 2]
+    # pair-iterations/s at the workload's mean level size, extrapolated linearly in points (stated)
+    value = (n_sample / pixels_per_pair_iter()) / t
+    sample = (f"1 pair x 1 BundleIteration at 160x120 (N={n_sample}), C={args.channels}, K={args.bases}, fp32, "
+              f"median of {len(times)} runs, extrapolated linearly in points to the mean level size")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
+            "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "reference_arm": "oracle port (TF-1.x reference cannot execute here)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return (f"cfg2: nb={args.nb}/GPU frame-pairs, dense levels 80x60..640x480, C={args.channels}, K={args.bases}, "
+            f"{args.iters} LM iters/level, lambda-MLP")
+
+
+# ----------------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    from banet_b200 import ops, synth, _lib
+    from banet_b200 import dist as bdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=dev)
+
+    C, K, nb, iters = args.channels, args.bases, args.nb, args.iters
+    sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 2 + 1000 * rank,
+                          device=dev, dtype=torch.float32)
+    levels = [ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B) for l in sc.levels]
+    g = torch.Generator().manual_seed(7)
+    dims = [C, 2 * C, 4 * C, 2 * C, C, 1]
+    packed = []
+    for _ in LEVEL_IDS:       # he-normal lambda-MLP, seed 7 (reference bundlenet.py:105)
+        params = [(torch.randn(dims[i], dims[i + 1], generator=g) * (2.0 / dims[i]) ** 0.5, torch.zeros(dims[i + 1])) for i in range(5)]
+        packed.append(ops.pack_mlp(params).to(dev))
+    ws = torch.empty(ops.lm_run_workspace_bytes(levels), dtype=torch.uint8, device=dev)
+    n_levels, total_iters = len(levels), len(levels) * iters
+
+    def step():
+        R, T, W, status = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws)
+        if world > 1:
+            return bdist.all_gather_solution(R, T, W), status
+        return (R, T, W), status
+
+    def barrier():
+        if world > 1:
+            td.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        out, status = step()
+    barrier()
+    assert int(status.abs().max()) == 0, "solver reported a non-SPD / non-finite system"
+
+    sampler = ClockSampler(local); sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out, status = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        td.all_reduce(tms, op=td.ReduceOp.MAX)
+        ms = float(tms.item())
+    ms_per_step = ms / args.steps
+    value = world * nb * total_iters / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (lm_build_kernel), per level, CUDA events on the launch stream ----
+    peak, peak_kind = measured_peaks()
+    per_level = []
+    for lv, sl in zip(levels, sc.levels):
+        for _ in range(2):
+            ops.lm_build(lv, sc.R0, sc.T0, sc.W0)
+        reps = 5
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(reps):
+            ops.lm_build(lv, sc.R0, sc.T0, sc.W0)
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps * 1e-3
+        by = nb * algorithmic_bytes_per_pair_iter(sl.N, C, K)
+        per_level.append({"level": f"{sl.w}x{sl.h}", "ms": t * 1e3, "alg_bytes": by, "gbs": by / t / 1e9})
+    top = per_level[-1]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "lm_build_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "lm_build_kernel (+lm_reduce_kernel) @640x480", "achieved": top["gbs"], "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": top["gbs"] / peak, "traffic": traffic, "per_level": per_level,
+                "all_levels_gbs": sum(p["alg_bytes"] for p in per_level) / sum(p["ms"] * 1e-3 for p in per_level) / 1e9}
+
+    # ---- e2e: host buffers -> device -> solve -> host, through the public API -------------------------------
+    e2e = None
+    if not args.no_e2e:
+        try:
+            e2e = run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters)
+        except Exception as ex:      # e.g. not enough pinnable host memory: report, do not fake
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, n_sample, cores = cpu_reference_sample(C, K, 4)
+        t = sorted(times)[len(times) // 2]
+        cpu_baseline = {"value": (n_sample / pixels_per_pair_iter()) / t, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"oracle materialised BundleIteration, 1 pair at 160x120 (N={n_sample}), fp32, median of {len(times)}, "
+                                  f"{t:.2f} s each, extrapolated linearly in points"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args), "global_pairs": world * nb, "lm_iterations_per_step": total_iters,
+                           "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": "fp32-simt",
+                           "l2": "inputs (~33 GB/GPU) far exceed the 126 MB L2; no flush needed",
+                           "parallelism": f"pairs sharded over {world} GPU(s), one all-gather of (R,T,W) per step"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 5),
+                "roofline": roofline, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters):
+    from banet_b200 import ops
+    from banet_b200 import dist as bdist
+    host = []
+    h2d = 0
+    for l in sc.levels:
+        tens = {}
+        for name in ("conv1", "conv2", "intr", "p", "D", "B"):
+            t = getattr(l, name)
+            ht = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+            ht.copy_(t)
+            tens[name] = ht; h2d += ht.numel() * 4
+        host.append(tens)
+    hR = sc.R0.cpu().pin_memory(); hT = sc.T0.cpu().pin_memory(); hW = sc.W0.cpu().pin_memory()
+    h2d += (hR.numel() + hT.numel() + hW.numel()) * 4
+    oR = torch.empty_like(hR).pin_memory(); oT = torch.empty_like(hT).pin_memory(); oW = torch.empty_like(hW).pin_memory()
+    d2h = (oR.numel() + oT.numel() + oW.numel()) * 4 * world
+
+    def e2e_step():
+        lvls = []
+        for l, tens in zip(sc.levels, host):
+            for name, ht in tens.items():
+                getattr(l, name).copy_(ht, non_blocking=True)           # host -> device, every step
+            lvls.append(ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B))
+        R0 = hR.to(dev, non_blocking=True); T0 = hT.to(dev, non_blocking=True); W0 = hW.to(dev, non_blocking=True)
+        R, T, W, status = ops.lm_run(lvls, args.iters, R0, T0, W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws)
+        if world > 1:
+            R, T, W = bdist.all_gather_solution(R, T, W)
+            return R.cpu(), T.cpu(), W.cpu()
+        oR.copy_(R, non_blocking=True); oT.copy_(T, non_blocking=True); oW.copy_(W, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return oR, oT, oW
+
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        import torch.distributed as td
+        td.barrier(device_ids=[local])
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        td.all_reduce(tms, op=td.ReduceOp.MAX); ms = float(tms.item())
+    per = ms / args.e2e_steps * 1e-3
+    return {"value": world * args.nb * total_iters / per, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+            "d2h_bytes_per_step": d2h, "ms_per_step": per * 1e3, "steps": args.e2e_steps,
+            "note": "pinned host -> device copy of every level tensor + solve + device -> host of (R,T,W) per step"}
+
+
+if __name__ == "__main__":
+    main()

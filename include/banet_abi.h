@@ -1,0 +1,155 @@
+/*
+ * banet_abi.h — C-ABI of libbanet_sm100.so: the B200 (sm_100a) drop-in for the BA layer's inner
+ * Levenberg–Marquardt loop of frobelbest/BANet.  Plain pointers and sizes only; no torch / TF types.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (fp32 unless stated), row-major contiguous, laid out exactly
+ *     like the reference tensors named beside it; `stream` is a cudaStream_t passed as void*;
+ *   - the library allocates nothing and keeps no global state (contrast reference utils.cu:210-216,
+ *     259-296: process-static persistent scratch); the caller owns outputs and workspaces;
+ *   - every call is asynchronous on `stream` and returns 0 (BANET_OK) or a negative error code;
+ *     banet_last_error() gives a thread-local message (reference ignores BLAS status, utils.cu:331);
+ *   - per-pair numeric trouble (non-positive pivot, NaN) is reported in a device-side `status[nb]`.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef BANET_ABI_H_
+#define BANET_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BANET_ABI_VERSION 1
+
+#define BANET_OK               0
+#define BANET_ERR_BAD_ARG     (-1)
+#define BANET_ERR_WORKSPACE   (-2)
+#define BANET_ERR_CUDA        (-3)
+#define BANET_ERR_UNSUPPORTED (-4)
+
+typedef void* banet_stream_t;            /* cudaStream_t */
+
+int         banet_abi_version(void);
+const char* banet_last_error(void);
+/* 0 if the current CUDA device can run this library (compute capability 10.x), else an error. */
+int         banet_device_check(void);
+int         banet_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Op level — the reference's own native boundary.
+ *     Replaces TF op `EquationConstruction` (utils.cu:150-171 op, :219-417 kernel; loaded
+ *     bundlenet.py:76-77):   left[b] = sum_n J^T G^T G J,  right[b] = sum_n J^T G^T d.
+ *       J [nb,N,2,P]  G [nb,N,C,2]  d [nb,N,C,1]  ->  AtA [nb,P,P]  Atb [nb,P,1]
+ * ---------------------------------------------------------------------------------------------- */
+size_t banet_eqc_workspace_bytes(int nb, int N, int C, int P);
+int    banet_eqc_fwd(const float* J, const float* G, const float* d, int nb, int N, int C, int P,
+                     float* AtA, float* Atb, void* ws, size_t ws_bytes, banet_stream_t stream);
+
+/*     Replaces TF op `EquationConstructionGrad` (utils.cu:420-428 op, :465-694 kernel; registered as
+ *     the gradient in bundlenet.py:79-82).  With A = G J:
+ *       dA = 2 A Ghat + d ghat^T (utils.cu:648-668)   dd = A ghat (:636-645)
+ *       dJ = G^T dA (:670-679)                         dG = dA J^T (:681-690)
+ *     exact_sym = 0 reproduces the reference (2*A*Ghat); exact_sym = 1 uses A (Ghat + Ghat^T), the
+ *     true adjoint for a non-symmetric upstream gradient.  No workspace needed. */
+int    banet_eqc_bwd(const float* J, const float* G, const float* d,
+                     const float* gAtA, const float* gAtb, int nb, int N, int C, int P, int exact_sym,
+                     float* dJ, float* dG, float* dd, banet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Pre-steps of a level.
+ * ---------------------------------------------------------------------------------------------- */
+/* BundleNet.computeCoordinates (bundlenet.py:112-120; un-normalised legacy/ba.py:27-34).
+ *   points [nb,N,2], intr [nb,4]=(fx,fy,ox,oy) -> p [nb,3,N]   (L2-normalised iff normalize!=0) */
+int banet_compute_coordinates(const float* points, const float* intr, int nb, int N, int normalize,
+                              float* p, banet_stream_t stream);
+/* BundleNet.grad_fixed + concat (bundlenet.py:92-100, 388-389), optionally fused with the
+ * half-swap pairing of :386 (swap_halves!=0: output pair b reads input pair (b + nb/2) % nb).
+ *   F [nb,h,w,C] -> conv2 [nb,h,w,3C] = [F | gradx | grady] */
+int banet_grad_fixed_concat(const float* F, int nb, int h, int w, int C, int swap_halves,
+                            float* conv2, banet_stream_t stream);
+/* tf.contrib.resampler.resampler (call sites bundlenet.py:290,320,343,344,385): bilinear, zero outside.
+ *   data [nb,h,w,C], xy [nb,N,2] (sampled at xy*coord_scale) -> out [nb,N,C] */
+int banet_resample(const float* data, const float* xy, float coord_scale, int nb, int h, int w, int C, int N,
+                   float* out, banet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Layer level — one LM iteration = BundleNet.BundleIteration (bundlenet.py:193-278) or
+ *     BundleNet.CameraIteration (:122-191) when K == 0 / B == NULL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct banet_level {
+    int nb, N, C, K;          /* pairs, points per pair, feature channels, depth bases (0 = pose only) */
+    int h, w;                 /* conv2 map size at this level */
+    int conv2_channels;       /* 3*C: [F2|gx|gy] as in the reference; C: F2 only, gradients derived on the fly */
+    const float* conv1;       /* [nb,N,C]      bundlenet.py:385 */
+    const float* conv2;       /* [nb,h,w,conv2_channels]  :386-389 */
+    const float* intr;        /* [nb,4] fx,fy,ox,oy at this level (reference tiles them to [nb,N], :379-382) */
+    const float* p;           /* [nb,3,N]      :358 */
+    const float* D;           /* [nb,N,1]      :343 */
+    const float* B;           /* [nb,N,K] or NULL  :344 */
+} banet_level_t;
+
+#define BANET_PREC_FP32_SIMT 0   /* every contraction in fp32 FFMA (reference-exact arithmetic type)   */
+#define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32, operands rounded to nearest    */
+#define BANET_PREC_TF32X2    2   /* split-A two-term tf32 (near-fp32)                                   */
+
+/* Normal equations + damping statistics of one iteration (bundlenet.py:206-239, 259-263 and the
+ * mean-|diff| of :243), fused: J, G, d are never materialised.
+ *   R [nb,3,3], T [nb,3,1], W [nb,K,1] ->
+ *   H [nb,P,P] (= AtA), g [nb,P] (= Atb), rbar_sum [nb,C] (= sum_n |diff|, NOT yet divided by N),
+ *   nvalid [nb] (in-bounds point count, as float).   P = 6 + K. */
+size_t banet_lm_build_workspace_bytes(const banet_level_t* lv, int precision);
+int    banet_lm_build(const banet_level_t* lv, const float* R, const float* T, const float* W,
+                      int precision, float* H, float* g, float* rbar_sum, float* nvalid,
+                      void* ws, size_t ws_bytes, banet_stream_t stream);
+
+/* lambda prediction (bundlenet.py:241-253; pose-only :165-173): rbar = rbar_sum/N, 5 dense layers
+ * C->2C->4C->2C->C->1 (selu x4, tanh), lambda = base * ||rbar||_2^(2+h).
+ *   mlp_weights: the 5 filters [cin,cout] then... see banet_mlp_param_count(); packed
+ *   [W1,b1,W2,b2,...,W5,b5] in one buffer, W_i row-major [cin,cout] (TF conv1d filter [1,cin,cout]).
+ *   base: l2_regularizer_base (1000 in :393; pass 1 for CameraIteration, which ignores it). */
+size_t banet_mlp_param_count(int C);
+int    banet_lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp_weights, float base,
+                       float* lambda_out, banet_stream_t stream);
+
+typedef struct banet_solve_opts {
+    float damping_eps;          /* 1e-5  (bundlenet.py:182,266) */
+    int   undamped_last;        /* 1 for BundleIteration (:266 leaves the last depth coefficient undamped); 0 for CameraIteration */
+    int   vmatrix_batch_scramble; /* 0: per-pair V; 1: reproduce the axis-0 stack of bundlenet.py:45 literally (nb>1 interleaves pairs) */
+} banet_solve_opts_t;
+
+/* Damping + solve + update (bundlenet.py:264-276; pose-only :181-190).  tf.matrix_solve (LU) is
+ * replaced by an in-shared-memory Cholesky (the damped normal matrix is SPD).
+ *   H,g,lambda[nb], R,T,W -> R',T',W' (may alias the inputs), delta [nb,P] (the solution, optional/NULL),
+ *   status [nb] int32: 0 ok, 1 non-positive pivot (matrix not SPD), 2 non-finite input. */
+size_t banet_lm_solve_workspace_bytes(int nb, int K);
+int    banet_lm_solve_update(const float* H, const float* g, const float* lambda, int nb, int K,
+                             const banet_solve_opts_t* opts,
+                             const float* R, const float* T, const float* W,
+                             float* R_out, float* T_out, float* W_out, float* delta, int32_t* status,
+                             void* ws, size_t ws_bytes, banet_stream_t stream);
+
+/* Whole coarse-to-fine solve: for each level, `iters_per_level` iterations of
+ * build -> lambda -> solve/update, with W carried across levels (the level loop of
+ * bundlenet.py:376-399 with the iteration count of legacy/ba.py:106-121).
+ *   mlp_weights[l]: packed lambda-MLP of level l, or NULL with lambda_fixed >= 0 to bypass the MLP.
+ *   R,T,W are updated in place.  status [nb] accumulates (bitwise or) the per-iteration status. */
+size_t banet_lm_run_workspace_bytes(const banet_level_t* levels, int nlevels, int precision);
+int    banet_lm_run(const banet_level_t* levels, int nlevels, int iters_per_level,
+                    const float* const* mlp_weights, float l2_regularizer_base, float lambda_fixed,
+                    const banet_solve_opts_t* opts, int precision,
+                    float* R, float* T, float* W, int32_t* status,
+                    void* ws, size_t ws_bytes, banet_stream_t stream);
+
+/* Final depth composition of BundleResize (bundlenet.py:397): out = init_depth + basis . W
+ *   basis [nb,M,K] (M = h/2*w/2), W [nb,K,1], init_depth [nb,M] -> out [nb,M] */
+int banet_depth_compose(const float* init_depth, const float* basis, const float* W, int nb, int M, int K,
+                        float* out, banet_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BANET_ABI_H_ */
