@@ -260,7 +260,8 @@ def test_full_size_properties():
     additivity over pixel subsets (H(all) == H(first half) + H(second half)), symmetry, determinism."""
     ops = _ops()
     from banet_b200 import synth
-    sc = synth.make_scene(nb=1, H=480, W=640, C=128, K=128, level_ids=(3,), seed=77, device="cuda", dtype=torch.float32)
+    sc = synth.make_scene(nb=1, H=480, W=640, C=128, K=128, level_ids=(3,), seed=77, device="cuda", dtype=torch.float32,
+                          rot_deg=0.03, trans_m=0.002, start_trans_noise_m=0.001)      # inside the fine level's basin
     lv = sc.levels[0]
     full = ops.Level(lv.conv1, lv.conv2, lv.intr, lv.p, lv.D, lv.B)
     H, g, rbar, nv = ops.lm_build(full, sc.R0, sc.T0, sc.W0)
