@@ -60,6 +60,7 @@ SIGNATURES = {
                                C.POINTER(BanetSolveOpts), C.c_int] + [c_float_p] * 3 + [C.c_void_p]
                      + [C.c_void_p, C.c_size_t, c_stream]),
     "banet_depth_compose": (C.c_int, [c_float_p] * 3 + [C.c_int] * 3 + [c_float_p, c_stream]),
+    "banet_tc_selftest": (C.c_int, [c_float_p] * 3 + [C.c_int, C.c_int, c_stream]),
 }
 
 _lib: Optional[C.CDLL] = None

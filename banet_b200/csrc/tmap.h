@@ -1,0 +1,45 @@
+// Host-side creation of TMA tensor maps through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "common.cuh"
+
+namespace banet {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled()
+{
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+// fp32 matrix [rows, cols] row-major (cols contiguous); box = box_cols x box_rows, 128B swizzle with 32-byte atoms
+// (the layout tcgen05 kind::tf32 needs for MN-major operands); box_cols*4 must be 128.
+inline int make_tmap_f32_2d_sw128_32b(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols)
+{
+    PFN_encodeTiled enc = get_encode_tiled();
+    BANET_REQUIRE(enc, BANET_ERR_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstr[1] = {cols * sizeof(float)};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    BANET_REQUIRE(r == CUDA_SUCCESS, BANET_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu", (int)r,
+                  (unsigned long long)rows, (unsigned long long)cols);
+    return BANET_OK;
+}
+
+}  // namespace banet

@@ -149,6 +149,11 @@ int    banet_lm_run(const banet_level_t* levels, int nlevels, int iters_per_leve
 int banet_depth_compose(const float* init_depth, const float* basis, const float* W, int nb, int M, int K,
                         float* out, banet_stream_t stream);
 
+/* Diagnostic (not part of the reference's interface): one 64-pixel k-tile through the TMA + tcgen05 building
+ * blocks of the tensor-core build path.  A [64,128], R [64,160] -> D [128,160] = A^T R.
+ * mode 0: single tf32 pass; mode 1: split-A two-pass.  use_rna: round R to tf32 (nearest) first. */
+int banet_tc_selftest(const float* A, const float* R, float* D, int mode, int use_rna, banet_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
