@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbanet_sm100.so")
 
 BANET_OK = 0
-PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2 = 0, 1, 2
+PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2 = -1, 0, 1, 2
 
 c_float_p = C.c_void_p      # raw device pointers
 c_stream = C.c_void_p

@@ -35,6 +35,33 @@ static int check_level(const banet_level_t* lv, const char* who)
     return BANET_OK;
 }
 
+int resolve_precision(const banet_level_t* lv, int precision)
+{
+    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X2 : BANET_PREC_FP32_SIMT;
+    if (precision == BANET_PREC_FP32_SIMT) return precision;
+    if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2) {
+        if (!tc_supported(lv)) {
+            set_error("precision mode %d (tensor cores) needs K=128, C in {64,128} and 16-B aligned tensors; got K=%d C=%d", precision, lv->K, lv->C);
+            return BANET_ERR_UNSUPPORTED;
+        }
+        return precision;
+    }
+    set_error("unknown precision mode %d", precision);
+    return BANET_ERR_BAD_ARG;
+}
+
+int plan_for(const banet_level_t* lv, int resolved, BuildPlan* plan)
+{
+    return resolved == BANET_PREC_FP32_SIMT ? build_plan(lv, num_sms(), plan) : build_plan_tc(lv, num_sms(), plan);
+}
+
+int build_dispatch(const banet_level_t* lv, int resolved, const BuildPlan& plan, const float* R, const float* T, const float* W,
+                   float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st)
+{
+    if (resolved == BANET_PREC_FP32_SIMT) return lm_build_simt(lv, plan, R, T, W, H, g, rbar_sum, nvalid, ws, st);
+    return lm_build_tc(lv, plan, resolved == BANET_PREC_TF32X2 ? 2 : 1, R, T, W, H, g, rbar_sum, nvalid, ws, st);
+}
+
 }  // namespace banet
 
 using namespace banet;
@@ -58,10 +85,11 @@ extern "C" int banet_device_check(void)
 // -------------------------------------------------------------------------------------------------
 extern "C" size_t banet_lm_build_workspace_bytes(const banet_level_t* lv, int precision)
 {
-    (void)precision;
     if (!lv) return 0;
+    const int res = resolve_precision(lv, precision);
+    if (res < 0) return 0;
     BuildPlan plan;
-    if (build_plan(lv, num_sms(), &plan) != BANET_OK) return 0;
+    if (plan_for(lv, res, &plan) != BANET_OK) return 0;
     return plan.ws_bytes;
 }
 
@@ -72,12 +100,13 @@ extern "C" int banet_lm_build(const banet_level_t* lv, const float* R, const flo
     if (rc) return rc;
     BANET_REQUIRE(R && T && H && g && rbar_sum && nvalid, BANET_ERR_BAD_ARG, "lm_build: null pointer");
     BANET_REQUIRE(lv->K == 0 || W, BANET_ERR_BAD_ARG, "lm_build: K=%d but W is null", lv->K);
-    BANET_REQUIRE(precision == BANET_PREC_FP32_SIMT, BANET_ERR_UNSUPPORTED, "lm_build: precision mode %d not available in this build", precision);
+    const int res = resolve_precision(lv, precision);
+    if (res < 0) return res;
     BuildPlan plan;
-    rc = build_plan(lv, num_sms(), &plan);
+    rc = plan_for(lv, res, &plan);
     if (rc) return rc;
     BANET_REQUIRE(ws && ws_bytes >= plan.ws_bytes, BANET_ERR_WORKSPACE, "lm_build: workspace %zu < %zu bytes", ws_bytes, plan.ws_bytes);
-    return lm_build_simt(lv, plan, R, T, W, H, g, rbar_sum, nvalid, ws, (cudaStream_t)stream);
+    return build_dispatch(lv, res, plan, R, T, W, H, g, rbar_sum, nvalid, ws, (cudaStream_t)stream);
 }
 
 extern "C" size_t banet_mlp_param_count(int C) { return (size_t)20 * C * C + (size_t)10 * C + 1; }
@@ -117,12 +146,13 @@ namespace {
 struct RunCarve { size_t build, H, g, rbar, nvalid, lambda, delta, total; };
 int carve(const banet_level_t* levels, int nlevels, int precision, RunCarve* c)
 {
-    (void)precision;
     size_t build = 0; int maxC = 0;
     const int nb = levels[0].nb, K = levels[0].K, P = 6 + K;
     for (int l = 0; l < nlevels; ++l) {
         BuildPlan plan;
-        int rc = build_plan(&levels[l], num_sms(), &plan);
+        const int res = resolve_precision(&levels[l], precision);
+        if (res < 0) return res;
+        int rc = plan_for(&levels[l], res, &plan);
         if (rc) return rc;
         if (plan.ws_bytes > build) build = plan.ws_bytes;
         if (levels[l].C > maxC) maxC = levels[l].C;
@@ -156,7 +186,6 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
                             float* R, float* T, float* W, int32_t* status, void* ws, size_t ws_bytes, banet_stream_t stream)
 {
     BANET_REQUIRE(levels && nlevels > 0 && iters_per_level > 0 && opts && R && T && status, BANET_ERR_BAD_ARG, "lm_run: bad argument");
-    BANET_REQUIRE(precision == BANET_PREC_FP32_SIMT, BANET_ERR_UNSUPPORTED, "lm_run: precision mode %d not available in this build", precision);
     const int nb = levels[0].nb, K = levels[0].K;
     for (int l = 0; l < nlevels; ++l) {
         int rc = check_level(&levels[l], "lm_run");
@@ -182,12 +211,14 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
     for (int l = 0; l < nlevels; ++l) {
         const banet_level_t* lv = &levels[l];
         BuildPlan plan;
-        rc = build_plan(lv, num_sms(), &plan);
+        const int res = resolve_precision(lv, precision);
+        if (res < 0) return res;
+        rc = plan_for(lv, res, &plan);
         if (rc) return rc;
         const bool use_mlp = mlp_weights && mlp_weights[l] && lambda_fixed < 0.f;
         if (!use_mlp) fill_kernel<<<(nb + 255) / 256, 256, 0, st>>>(lam, nb, lambda_fixed);
         for (int it = 0; it < iters_per_level; ++it) {
-            rc = lm_build_simt(lv, plan, R, T, W, H, g, rbar, nvalid, base + c.build, st);
+            rc = build_dispatch(lv, res, plan, R, T, W, H, g, rbar, nvalid, base + c.build, st);
             if (rc) return rc;
             if (use_mlp) {
                 rc = lm_lambda(rbar, nb, lv->N, lv->C, mlp_weights[l], l2_regularizer_base, lam, st);

@@ -420,6 +420,13 @@ lm_reduce_kernel(const BuildParams prm, int grid_build, float* __restrict__ H, f
     }
 }
 
+int launch_lm_reduce(const BuildParams& prm, int grid_build, float* H, float* g, float* rbar_sum, float* nvalid, cudaStream_t st)
+{
+    lm_reduce_kernel<<<prm.nb, 256, 0, st>>>(prm, grid_build, H, g, rbar_sum, nvalid);
+    BANET_CUDA_LAUNCH_CHECK("lm_reduce_kernel launch");
+    return BANET_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 static int padded_K(int K) {
     if (K == 0) return 0;
@@ -488,9 +495,7 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
     }
 #undef BANET_DISPATCH
     if (rc != BANET_OK) return rc;
-    lm_reduce_kernel<<<lv->nb, 256, 0, st>>>(prm, plan.grid, H, g, rbar_sum, nvalid);
-    BANET_CUDA_LAUNCH_CHECK("lm_reduce_kernel launch");
-    return BANET_OK;
+    return launch_lm_reduce(prm, plan.grid, H, g, rbar_sum, nvalid, st);
 }
 
 }  // namespace banet

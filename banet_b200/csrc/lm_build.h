@@ -25,6 +25,20 @@ int build_plan(const banet_level_t* lv, int num_sms, BuildPlan* plan);
 int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R, const float* T, const float* W,
                   float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st);
 
+int launch_lm_reduce(const BuildParams& prm, int grid_build, float* H, float* g, float* rbar_sum, float* nvalid, cudaStream_t st);
+
+// tensor-core path (lm_build_tc.cu): K = 128, C in {64,128}
+bool tc_supported(const banet_level_t* lv);
+int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan);
+int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const float* R, const float* T, const float* W,
+                float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st);
+
+// precision resolution + dispatch (abi.cu)
+int resolve_precision(const banet_level_t* lv, int precision);      // -> BANET_PREC_* actually used, or <0 (error set)
+int plan_for(const banet_level_t* lv, int resolved, BuildPlan* plan);
+int build_dispatch(const banet_level_t* lv, int resolved, const BuildPlan& plan, const float* R, const float* T, const float* W,
+                   float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st);
+
 // lambda MLP / solve / update (lm_solve.cu)
 int lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp, float base, float* lambda_out, cudaStream_t st);
 int lm_solve_update(const float* H, const float* g, const float* lambda, int nb, int K, const banet_solve_opts_t& opts,

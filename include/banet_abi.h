@@ -92,9 +92,10 @@ typedef struct banet_level {
     const float* B;           /* [nb,N,K] or NULL  :344 */
 } banet_level_t;
 
+#define BANET_PREC_AUTO    (-1)   /* TF32X2 where the tensor-core path applies (K=128, C in {64,128}), else FP32_SIMT */
 #define BANET_PREC_FP32_SIMT 0   /* every contraction in fp32 FFMA (reference-exact arithmetic type)   */
-#define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32, operands rounded to nearest    */
-#define BANET_PREC_TF32X2    2   /* split-A two-term tf32 (near-fp32)                                   */
+#define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32: basis truncated by the tensor core, s*b rounded to nearest */
+#define BANET_PREC_TF32X2    2   /* split-A two-pass tf32: b = trunc(b) + (b - trunc(b)); only s*b's rounding remains             */
 
 /* Normal equations + damping statistics of one iteration (bundlenet.py:206-239, 259-263 and the
  * mean-|diff| of :243), fused: J, G, d are never materialised.

@@ -47,3 +47,67 @@ def test_tcgen05_precision_modes(mode, use_rna, tol):
     err = rel_fro(D, A.double().t() @ R.double())
     print(f"mode={mode} rna={use_rna} rel-fro={err:.3e}")
     assert err < tol
+
+
+# ------------------------------------------------------------------------------------ full tensor-core build path
+from helpers import O, scene_case, oracle_level_inputs, to_cuda32
+
+
+def _build_case(C, fly, n_points, seed, nb=3, H=48, W=64):
+    from banet_b200 import ops
+    sc = scene_case(nb=nb, H=H, W=W, C=C, K=128, level_ids=(3,), seed=seed, n_points=n_points, dtype=torch.float32)
+    lv = sc.levels[0]
+    conv2 = lv.conv2[..., :C] if fly else lv.conv2
+    lvl = ops.Level(to_cuda32(lv.conv1), to_cuda32(conv2), to_cuda32(lv.intr), to_cuda32(lv.p), to_cuda32(lv.D), to_cuda32(lv.B))
+    Wt = sc.W0 + 0.01 * torch.randn(sc.W0.shape, generator=torch.Generator().manual_seed(1))
+    a = oracle_level_inputs(lv)
+    ref = O.normal_equations_structured(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"],
+                                        sc.R0.double(), sc.T0.double(), Wt.double())
+    return ops, sc, lvl, Wt, ref
+
+
+@pytest.mark.parametrize("C,fly,n_points", [(128, False, None), (128, True, None), (64, False, 1000), (64, True, 777), (128, False, 100)])
+@pytest.mark.parametrize("prec", [1, 2])
+def test_lm_build_tensorcore_matches_oracle(C, fly, n_points, prec):
+    ops, sc, lvl, Wt, (rH, rg, rrbar, rnv) = _build_case(C, fly, n_points, seed=40 + C + (n_points or 0))
+    H, g, rbar, nvalid = ops.lm_build(lvl, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(Wt), precision=prec)
+    Hs, gs, rbs, nvs = ops.lm_build(lvl, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(Wt), precision=0)
+    assert torch.equal(nvalid.cpu().double(), rnv)
+    eH, eg = rel_fro(H, rH), rel_fro(g, rg.squeeze(-1))
+    print(f"C={C} fly={fly} N={sc.levels[0].N} prec={prec}: relH={eH:.2e} relg={eg:.2e}  (simt: {rel_fro(Hs, rH):.2e} {rel_fro(gs, rg.squeeze(-1)):.2e})")
+    tol = 5e-4 if prec == 1 else 1e-4
+    assert eH < tol and eg < tol
+    # pose block and rbar do not go through the tensor cores: fp32-exact
+    assert rel_fro(H[:, :6, :6], rH[:, :6, :6]) < 2e-5 and rel_fro(g[:, :6], rg[:, :6, 0]) < 2e-5
+    assert rel_fro(rbar / sc.levels[0].N, rrbar.squeeze(1)) < 2e-5
+    assert torch.equal(H, H.transpose(1, 2))
+
+
+def test_lm_run_tensorcore_vs_oracle_outputs():
+    """Whole solve (2 levels x 3 iterations, fixed lambda, K=128) in every precision mode against the float64 oracle.
+    Bar: the 1e-4 north-star tolerance on R, T, W — or, where the problem is too ill-conditioned for ANY fp32
+    implementation, twice the error of the oracle itself run in float32 (the reference's arithmetic type)."""
+    from banet_b200 import ops
+    sc = scene_case(nb=2, H=96, W=128, C=64, K=128, level_ids=(2, 3), seed=91, dtype=torch.float32)
+    levels = [ops.Level(to_cuda32(l.conv1), to_cuda32(l.conv2), to_cuda32(l.intr), to_cuda32(l.p), to_cuda32(l.D), to_cuda32(l.B)) for l in sc.levels]
+
+    def oracle(dtype):
+        olv = []
+        for l in sc.levels:
+            a = oracle_level_inputs(l, dtype)
+            olv.append(O.LevelInputs(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"], []))
+        opts = O.IterOptions(lambda_override=torch.full((2,), 0.05, dtype=dtype))
+        return O.lm_solve(olv, 3, sc.R0.to(dtype), sc.T0.to(dtype), sc.W0.to(dtype), opts)
+
+    oR, oT, oW = oracle(torch.float64)
+    fR, fT, fW = oracle(torch.float32)
+    floor = (rel_fro(fR, oR), rel_fro(fT, oT), rel_fro(fW, oW))
+    print(f"oracle fp32 vs fp64 (noise floor): {floor[0]:.2e} {floor[1]:.2e} {floor[2]:.2e}")
+    for prec in (0, 2, 1):
+        R, T, W, status = ops.lm_run(levels, 3, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(sc.W0), lambda_fixed=0.05, precision=prec)
+        errs = (rel_fro(R, oR), rel_fro(T, oT), rel_fro(W, oW))
+        print(f"prec={prec}: rel-fro R,T,W = {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e}")
+        assert status.abs().max().item() == 0
+        if prec in (0, 2):
+            for e, f in zip(errs, floor):
+                assert e < max(1e-4, 2.0 * f)
