@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbanet_sm100.so")
 
 BANET_OK = 0
-PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2 = -1, 0, 1, 2
+PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2, PREC_TF32X3 = -1, 0, 1, 2, 3
 
 c_float_p = C.c_void_p      # raw device pointers
 c_stream = C.c_void_p
@@ -23,7 +23,8 @@ class BanetLevel(C.Structure):
     _fields_ = [("nb", C.c_int), ("N", C.c_int), ("C", C.c_int), ("K", C.c_int),
                 ("h", C.c_int), ("w", C.c_int), ("conv2_channels", C.c_int),
                 ("conv1", C.c_void_p), ("conv2", C.c_void_p), ("intr", C.c_void_p),
-                ("p", C.c_void_p), ("D", C.c_void_p), ("B", C.c_void_p)]
+                ("p", C.c_void_p), ("D", C.c_void_p), ("B", C.c_void_p),
+                ("grid_w", C.c_int), ("grid_h", C.c_int)]
 
 
 class BanetSolveOpts(C.Structure):
@@ -60,7 +61,7 @@ SIGNATURES = {
                                C.POINTER(BanetSolveOpts), C.c_int] + [c_float_p] * 3 + [C.c_void_p]
                      + [C.c_void_p, C.c_size_t, c_stream]),
     "banet_depth_compose": (C.c_int, [c_float_p] * 3 + [C.c_int] * 3 + [c_float_p, c_stream]),
-    "banet_tc_selftest": (C.c_int, [c_float_p] * 3 + [C.c_int, C.c_int, c_stream]),
+    "banet_tc_selftest": (C.c_int, [c_float_p] * 3 + [C.c_int, C.c_int, C.c_int, c_stream]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -32,14 +32,16 @@ static int check_level(const banet_level_t* lv, const char* who)
     BANET_REQUIRE(lv->conv1 && lv->conv2 && lv->intr && lv->p && lv->D, BANET_ERR_BAD_ARG, "%s: null tensor", who);
     BANET_REQUIRE(lv->K == 0 || lv->B, BANET_ERR_BAD_ARG, "%s: K=%d but B is null", who, lv->K);
     BANET_REQUIRE((long long)lv->h * lv->w * lv->conv2_channels < (1LL << 40), BANET_ERR_BAD_ARG, "%s: map too large", who);
+    BANET_REQUIRE((lv->grid_w == 0 && lv->grid_h == 0) || (lv->grid_w > 0 && lv->grid_h > 0 && (long long)lv->grid_w * lv->grid_h == lv->N),
+                  BANET_ERR_BAD_ARG, "%s: grid %dx%d does not match N=%d", who, lv->grid_w, lv->grid_h, lv->N);
     return BANET_OK;
 }
 
 int resolve_precision(const banet_level_t* lv, int precision)
 {
-    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X2 : BANET_PREC_FP32_SIMT;
+    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X3 : BANET_PREC_FP32_SIMT;
     if (precision == BANET_PREC_FP32_SIMT) return precision;
-    if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2) {
+    if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2 || precision == BANET_PREC_TF32X3) {
         if (!tc_supported(lv)) {
             set_error("precision mode %d (tensor cores) needs K=128, C in {64,128} and 16-B aligned tensors; got K=%d C=%d", precision, lv->K, lv->C);
             return BANET_ERR_UNSUPPORTED;
@@ -59,7 +61,7 @@ int build_dispatch(const banet_level_t* lv, int resolved, const BuildPlan& plan,
                    float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st)
 {
     if (resolved == BANET_PREC_FP32_SIMT) return lm_build_simt(lv, plan, R, T, W, H, g, rbar_sum, nvalid, ws, st);
-    return lm_build_tc(lv, plan, resolved == BANET_PREC_TF32X2 ? 2 : 1, R, T, W, H, g, rbar_sum, nvalid, ws, st);
+    return lm_build_tc(lv, plan, resolved, R, T, W, H, g, rbar_sum, nvalid, ws, st);
 }
 
 }  // namespace banet

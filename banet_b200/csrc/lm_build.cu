@@ -390,12 +390,14 @@ lm_reduce_kernel(const BuildParams prm, int grid_build, float* __restrict__ H, f
 
     const int nel = L.off_rbar() + C;
     for (int i = threadIdx.x; i < nel; i += blockDim.x) {
+        int src = i;                                        // element (r, cI) of H_dd lives at cI*K + r in a transposed slot
+        if (prm.hdd_transposed && i < L.off_ext()) { const int r = i / K, cI = i - r * K; src = cI * K + r; }
         double s = 0.0;
         for (int c = c0; c <= c1; ++c) {
             const long long tb = part_begin(prm.total_tiles, grid_build, c), te = part_begin(prm.total_tiles, grid_build, c + 1);
             if (tb >= te || te <= p0 || tb >= p1) continue;
             const int span = b - (int)(tb / prm.tiles_per_pair);
-            s += (double)prm.partials[((size_t)c * prm.max_span + span) * prm.slot_floats + i];
+            s += (double)prm.partials[((size_t)c * prm.max_span + span) * prm.slot_floats + src];
         }
         const float v = (float)s;
         if (i < L.off_ext()) {                              // H_dd: keep the lower triangle, mirror it
@@ -480,6 +482,7 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
     prm.partials = reinterpret_cast<float*>(ws);
     prm.slot_floats = plan.slot_floats; prm.max_span = plan.max_span;
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
+    prm.grid_w = 0; prm.grid_h = 0; prm.tiles_x = 0; prm.hdd_transposed = 0;
     const bool vec4 = (lv->C % 4 == 0) && (lv->conv2_channels % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(lv->conv1) | reinterpret_cast<uintptr_t>(lv->conv2)) % 16 == 0);
     int rc;

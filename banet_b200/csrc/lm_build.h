@@ -10,6 +10,8 @@ struct BuildParams {
     float* partials;
     int slot_floats, max_span, tiles_per_pair;
     long long total_tiles;
+    int grid_w, grid_h, tiles_x;      // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
+    int hdd_transposed;               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
 };
 
 struct BuildPlan {

@@ -8,15 +8,29 @@
 //        R  [64 px x 160]  row n = [ s_n * b_n (128) | v_n (6) | t_n | 0 ... ]  built by the gather warps = MN-major "B"
 //     => D[i][j<128] = H_dd[i][j],  D[i][128+r] = H_cd[r][i] (r<6),  D[i][134] = g_d[i]
 //
-// Precision: MODE 1 = one tf32 pass (A truncated by the tensor core, R rounded to nearest);
-//            MODE 2 = split-A: a second pass with A_lo = b - trunc(b), so only R's (unbiased) rounding remains.
+// Precision modes (tf32 keeps 10 mantissa bits; products are exact, accumulation is fp32):
+//   MODE 1  one pass:   A truncated by the tensor core, R rounded to nearest
+//   MODE 2  two passes: + A_lo = b - trunc(b)                       (only R's unbiased rounding remains)
+//   MODE 3  three passes: + R_lo = s*b - rna(s*b)                   (fp32-grade: the dropped term is ~2^-22)
 //
-// Warp roles (320 threads, 1 CTA / SM, persistent over a contiguous tile range):
-//   warp 0    TMA producer: basis tile -> smem stage (mbarrier complete_tx)
-//   warp 1    MMA issuer (one thread): 8 (16) tcgen05.mma per tile, tcgen05.commit frees the stage
-//   warps 2-9 gather warps: half-warp per pixel, lanes over channels: D~ = D + b.W (from the staged tile), warp,
-//             4-tap (or 12-texel, F2-only) gather, M/q reductions, per-pixel 2x7 algebra, R rows; at a pair
-//             boundary they drain TMEM (tcgen05.ld) into the partial slot.
+// Tiles: 64 points.  With the dense-grid hint (banet_level_t::grid_w/h) a tile is an 8x8 pixel patch fetched by ONE
+// 3-D TMA box and the gather warps' conv2 taps of a tile overlap (~1.3 texel fetches per pixel instead of ~2);
+// without the hint a tile is 64 consecutive points (2-D TMA box).
+//
+// TMEM accumulators: the tensor core TRUNCATES when it adds into the fp32 accumulator (measured: about -2.5e-8 relative
+// per accumulation step, tests/test_gpu_tensorcore.py::test_tcgen05_accumulator_rounding), so accumulation chains are kept
+// short: the hi-pass accumulates at most TC_CHAIN tiles into one of two ping-pong TMEM regions, which the gather warps
+// then drain (tcgen05.ld) and add, round-to-nearest, into the partial slot while the other region fills; the lo passes
+// (2^-11 of the magnitude) use a third region that is drained once per pair.
+//
+// Warp roles (384 threads = 3 warpgroups, 1 CTA / SM, persistent over a contiguous tile range):
+//   warp 0     TMA producer: basis tile -> smem stage (2 stages, mbarrier complete_tx)          } warpgroup 0 gives its
+//   warp 1     MMA issuer (one thread): 8 tcgen05.mma per pass and tile; tcgen05.commit         } registers away
+//   warps 2-3  idle                                                                            } (setmaxnreg.dec 40)
+//   warps 4-11 gather warps (setmaxnreg.inc 232), 8 pixels each per tile: D~ = D + b.W from the staged tile, thread-per-pixel warp geometry,
+//             then half-warp per pixel / lanes over channels for the 4-tap (or 12-texel, F2-only) gather with the loads of
+//             the next two (pixel pair, channel chunk) units in flight while the current one is reduced; per-pixel 2x7
+//             algebra; R rows; TMEM drains.
 #include "common.cuh"
 #include "lm_build.h"
 #include "tc_utils.cuh"
@@ -27,26 +41,31 @@ using namespace tc;
 
 constexpr int TC_TILE = 64;
 constexpr int TC_GW = 8;
-constexpr int TC_THREADS = (2 + TC_GW) * 32;
+constexpr int TC_GW0 = 4;                          // first gather warp (warpgroup 1)
+constexpr int TC_THREADS = (TC_GW0 + TC_GW) * 32;  // 384
+constexpr int TC_CHAIN = 4;                        // tiles per hi-accumulator chain
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_ACCL = 320;                       // TMEM column of the lo accumulator (hi: 0 and 160)
 constexpr int TC_K = 128;
 constexpr int TC_N = 160;
 constexpr int TC_STAGE_A = 4 * TC_TILE * 128;      // 32 KB: 4 blocks of [64 rows][128 B]
 constexpr int TC_STAGE_R = 5 * TC_TILE * 128;      // 40 KB
-constexpr int TC_REC = 16;                         // floats per pixel record
+constexpr int TC_REC = 12;                         // floats per pixel record
 
 template <int MODE> struct TcSmem {
-    static constexpr int off_A = 0;
-    static constexpr int off_R = 2 * TC_STAGE_A;
-    static constexpr int off_Alo = off_R + 2 * TC_STAGE_R;
-    static constexpr int off_misc = off_Alo + (MODE == 2 ? 2 * TC_STAGE_A : 0);
-    static constexpr int off_bar = off_misc;                       // 8 mbarriers
-    static constexpr int off_tmem = off_bar + 64;
-    static constexpr int off_pose = off_misc + 128;                // [2][16] floats
-    static constexpr int off_W = off_pose + 128;                   // [2][128] floats
-    static constexpr int off_rec = off_W + 1024;                   // [GW][8][TC_REC] floats
+    static constexpr int off_A = 0;                                   // 2 stages (TMA landing zone, also MMA operand A_hi)
+    static constexpr int off_R = 2 * TC_STAGE_A;                      // 1 stage
+    static constexpr int off_Alo = off_R + TC_STAGE_R;                // 1 stage (MODE >= 2)
+    static constexpr int off_Rlo = off_Alo + (MODE >= 2 ? TC_STAGE_A : 0);   // 1 stage (MODE 3)
+    static constexpr int off_misc = off_Rlo + (MODE == 3 ? TC_STAGE_R : 0);
+    static constexpr int off_bar = off_misc;                          // 12 mbarriers
+    static constexpr int off_tmem = off_bar + 96;
+    static constexpr int off_pose = off_misc + 128;                   // [2][16] floats
+    static constexpr int off_W = off_pose + 128;                      // [2][128] floats
+    static constexpr int off_rec = off_W + 1024;                      // [GW][8][TC_REC] floats
     static constexpr int off_cc = off_rec + TC_GW * 8 * TC_REC * 4;   // [GW][8][28] floats
     static constexpr int total = off_cc + TC_GW * 8 * 28 * 4;
-    static constexpr int bytes = total + 1024;                     // slack for manual 1024-B alignment
+    static constexpr int bytes = total + 1024;                        // slack for manual 1024-B alignment
 };
 
 __device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -58,6 +77,17 @@ __device__ __forceinline__ float hsum16(float v) {            // sum over the 16
     return v;
 }
 
+struct TileCoord { int b, n0, cnt, tx0, ty0; };
+
+__device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long long t) {
+    TileCoord tc;
+    tc.b = (int)(t / prm.tiles_per_pair);
+    const int r = (int)(t - (long long)tc.b * prm.tiles_per_pair);
+    if (prm.grid_w > 0) { const int tyi = r / prm.tiles_x; tc.ty0 = tyi * 8; tc.tx0 = (r - tyi * prm.tiles_x) * 8; tc.n0 = 0; tc.cnt = TC_TILE; }
+    else { tc.n0 = r * TC_TILE; tc.cnt = min(TC_TILE, prm.N - tc.n0); tc.tx0 = tc.ty0 = 0; }
+    return tc;
+}
+
 template <int NCH, bool FLY, int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams prm)
@@ -66,11 +96,14 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::off_bar);
-    uint64_t* fullB = bars;          // [2]
-    uint64_t* ready = bars + 2;      // [2]
-    uint64_t* empty = bars + 4;      // [2]
-    uint64_t* flushb = bars + 6;
-    uint64_t* tmemfree = bars + 7;
+    uint64_t* fullB = bars;          // [2]  TMA landed
+    uint64_t* emptyB = bars + 2;     // [2]  MMAs that read A stage s have completed
+    uint64_t* ready = bars + 4;      //      R (Alo, Rlo) of the current tile written by all gather warps
+    uint64_t* rfree = bars + 5;      //      MMAs of the current tile completed -> R may be overwritten
+    uint64_t* flushb = bars + 6;     //      every MMA of the span completed
+    uint64_t* tmemfree = bars + 7;   //      lo accumulator drained by the gather warps
+    uint64_t* chain_done = bars + 8; // [2]  every hi-pass MMA of the chain that used accumulator `set` completed
+    uint64_t* drained = bars + 10;   // [2]  hi accumulator `set` drained by the gather warps
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(base + SM::off_tmem);
     float* sPose = reinterpret_cast<float*>(base + SM::off_pose);
     float* sW = reinterpret_cast<float*>(base + SM::off_W);
@@ -79,23 +112,27 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = prm.N, h = prm.h, w = prm.w, c2 = prm.c2;
+    const bool grid2d = prm.grid_w > 0;
     constexpr int C = 64 * NCH;
     const long long t_begin = part_begin(prm.total_tiles, gridDim.x, blockIdx.x);
     const long long t_end   = part_begin(prm.total_tiles, gridDim.x, blockIdx.x + 1);
 
     if (tid == 0) {
         mbar_init(&fullB[0], 1); mbar_init(&fullB[1], 1);
-        mbar_init(&ready[0], TC_GW); mbar_init(&ready[1], TC_GW);
-        mbar_init(&empty[0], 1); mbar_init(&empty[1], 1);
+        mbar_init(&emptyB[0], 1); mbar_init(&emptyB[1], 1);
+        mbar_init(ready, TC_GW); mbar_init(rfree, 1);
         mbar_init(flushb, 1); mbar_init(tmemfree, TC_GW);
+        mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1);
+        mbar_init(&drained[0], TC_GW); mbar_init(&drained[1], TC_GW);
         fence_barrier_init();
         prefetch_tmap(&tmapB);
     }
-    if (warp == 0) tmem_alloc<256>(s_tmem);
-    // the pad chunks of R's 5th block (columns 136..159) stay zero for the whole kernel
-    for (int i = tid; i < 2 * TC_TILE * 8; i += TC_THREADS) {
-        const int s = i / (TC_TILE * 8), r = (i / 8) % TC_TILE, c = i & 7;
-        *reinterpret_cast<float4*>(base + SM::off_R + s * TC_STAGE_R + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (warp == 0) tmem_alloc<TC_TMEM_COLS>(s_tmem);
+    // the pad chunks of the 5th block of R / R_lo (columns 136..159) stay zero for the whole kernel
+    for (int i = tid; i < TC_TILE * 8; i += TC_THREADS) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<float4*>(base + SM::off_R + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 3) *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -103,88 +140,129 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
     tc_fence_after_sync();
     const uint32_t tmem = *s_tmem;
 
-    if (warp == 0) {
+    if (warp < TC_GW0) {
+      setmaxnreg_dec<40>();
+      if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             int it = 0;
             for (long long t = t_begin; t < t_end; ++t, ++it) {
                 const int s = it & 1, ph = (it >> 1) & 1;
-                const int b = (int)(t / prm.tiles_per_pair);
-                const int n0 = (int)(t - (long long)b * prm.tiles_per_pair) * TC_TILE;
-                mbar_wait(&empty[s], ph ^ 1);
+                const TileCoord tc = tile_coord(prm, t);
+                mbar_wait_sleep(&emptyB[s], ph ^ 1);
                 mbar_arrive_expect_tx(&fullB[s], TC_STAGE_A);
-                const int row = b * N + n0;
+                unsigned char* dst = base + SM::off_A + s * TC_STAGE_A;
+                if (grid2d) {
 #pragma unroll
-                for (int blk = 0; blk < 4; ++blk)
-                    tma_load_2d(base + SM::off_A + s * TC_STAGE_A + blk * 8192, &tmapB, blk * 32, row, &fullB[s]);
+                    for (int blk = 0; blk < 4; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[s]);
+                } else {
+                    const int row = tc.b * N + tc.n0;
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[s]);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================================================================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, TC_N);
-            int it = 0, span = 0, cur_b = -1;
-            uint32_t acc = 0;
+            int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, set = 0;
+            uint32_t accH = 0, accL = 0;
+            const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
             for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1;
+                const int s = it & 1;
                 const int b = (int)(t / prm.tiles_per_pair);
                 if (b != cur_b) {
-                    if (cur_b >= 0) { mma_commit(flushb); ++span; }
-                    mbar_wait(tmemfree, (span & 1) ^ 1);          // TMEM drained by the previous span's flush
-                    tc_fence_after_sync();
-                    acc = 0; cur_b = b;
+                    if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++span; }
+                    mbar_wait_sleep(tmemfree, (span & 1) ^ 1);    // lo accumulator drained by the previous span's flush
+                    accL = 0; cur_b = b; tic = 0;
                 }
-                mbar_wait(&ready[s], ph);
+                if (tic == 0) {                                   // new hi chain on the other accumulator
+                    ++chain; set = chain & 1;
+                    mbar_wait_sleep(&drained[set], ((chain >> 1) & 1) ^ 1);
+                    accH = 0;
+                }
+                mbar_wait_sleep(ready, it & 1);
                 tc_fence_after_sync();
-                const uint32_t r0 = smem_u32(base + SM::off_R + s * TC_STAGE_R);
+                const uint32_t ahi = smem_u32(base + SM::off_A + s * TC_STAGE_A);
 #pragma unroll
-                for (int pass = 0; pass < (MODE == 2 ? 2 : 1); ++pass) {
-                    const uint32_t a0 = smem_u32(base + (pass ? SM::off_Alo : SM::off_A) + s * TC_STAGE_A);
+                for (int pass = 0; pass < MODE; ++pass) {
+                    const uint32_t a0 = (pass == 1) ? alo : ahi;
+                    const uint32_t r0 = (pass == 2) ? rlo : rhi;
+                    const uint32_t dcol = tmem + (pass == 0 ? set * TC_N : TC_ACCL);
 #pragma unroll
                     for (int kk = 0; kk < TC_TILE / 8; ++kk) {
-                        mma_tf32_ss(tmem, make_desc_mn_sw128_32b(a0 + kk * 1024, 8192, 512),
-                                    make_desc_mn_sw128_32b(r0 + kk * 1024, 8192, 512), idesc, acc);
-                        acc = 1;
+                        mma_tf32_ss(dcol, make_desc_mn_sw128_32b(a0 + kk * 1024, 8192, 512),
+                                    make_desc_mn_sw128_32b(r0 + kk * 1024, 8192, 512), idesc, pass == 0 ? accH : accL);
+                        if (pass == 0) accH = 1; else accL = 1;
                     }
                 }
-                mma_commit(&empty[s]);
+                mma_commit(&emptyB[s]);
+                mma_commit(rfree);
+                if (++tic == TC_CHAIN) { mma_commit(&chain_done[set]); tic = 0; }
             }
-            if (cur_b >= 0) mma_commit(flushb);
+            if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); }
         }
+      }     // warps 2,3 of warpgroup 0 idle
     } else {
         // ===================================================================== gather warps
-        const int g = warp - 2, hw = lane >> 4, hl = lane & 15;
-        const int gtid = tid - 64;
+        setmaxnreg_inc<232>();
+        const int g = warp - TC_GW0, hw = lane >> 4, hl = lane & 15;
+        const int gtid = tid - TC_GW0 * 32;
         const int blkA = hl >> 3, ccA = hl & 7;                 // this lane's two 16-B chunks of a 128-float row: blocks blkA and 2+blkA
         float wreg[8];
         float rb[NCH * 4];
         float* myRec = sRec + g * 8 * TC_REC;
         float* myCC = sCC + (g * 8 + (lane & 7)) * 28;
         const SlotLayout L{TC_K, C};
-        int it = 0, span = 0, cur_b = -1;
+        unsigned char* Rs = base + SM::off_R;
+        int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, next_drain = 0;
+        bool first_drain = true;
 
-        auto flush = [&](int sp) {
-            float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
-            mbar_wait(flushb, sp & 1);
-            tc_fence_after_sync();
+        // add (or store) this warp's share of a 128 x 160 TMEM region into the slot: H_dd transposed (coalesced), ext rows
+        auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
             const int q = warp & 3, row = q * 32 + lane;
-            const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+            const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + col0;
             float v[32];
 #pragma unroll 1
             for (int cbi = 0; cbi < 2; ++cbi) {
                 const int cb = (g >= 4 ? 2 : 0) + cbi;
                 tmem_ld_32x32(tq + cb * 32, v);
-                float4* dst = reinterpret_cast<float4*>(slot + (size_t)row * TC_K + cb * 32);
+                float* dst = slot + (size_t)(cb * 32) * TC_K + row;
+                if (overwrite) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_K] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_K] += v[j];
+                }
             }
             if (g < 4) {
                 tmem_ld_32x32(tq + 128, v);
+                float* dst = slot + L.off_ext() + row;
 #pragma unroll
-                for (int r = 0; r < 7; ++r) slot[L.off_ext() + r * TC_K + row] = v[r];
+                for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * TC_K] = v[r]; else dst[r * TC_K] += v[r]; }
             }
+        };
+        auto drain_hi = [&](int c, float* slot) {
+            const int set = c & 1;
+            mbar_wait(&chain_done[set], (c >> 1) & 1);
+            tc_fence_after_sync();
+            drain_region(slot, set * TC_N, first_drain);
+            first_drain = false;
             tc_fence_before_sync();
-            // rbar / cc through a scratch aliased on R stage 0 (every MMA of this span has completed)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained[set]);
+        };
+
+        auto flush = [&](int sp) {
+            float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
+            for (; next_drain <= chain; ++next_drain) drain_hi(next_drain, slot);
+            mbar_wait(flushb, sp & 1);
+            tc_fence_after_sync();
+            if constexpr (MODE >= 2) drain_region(slot, TC_ACCL, false);
+            tc_fence_before_sync();
+            // rbar / cc through a scratch aliased on R (every MMA of this span has completed)
             float* scratch = reinterpret_cast<float*>(base + SM::off_R);
 #pragma unroll
             for (int u = 0; u < NCH * 4; ++u) rb[u] += __shfl_xor_sync(0xffffffffu, rb[u], 16);
@@ -212,11 +290,11 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
 
         for (long long t = t_begin; t < t_end; ++t, ++it) {
             const int s = it & 1, ph = (it >> 1) & 1;
-            const int b = (int)(t / prm.tiles_per_pair);
-            const int n0 = (int)(t - (long long)b * prm.tiles_per_pair) * TC_TILE;
-            const int cnt = min(TC_TILE, N - n0);
+            const TileCoord tc = tile_coord(prm, t);
+            const int b = tc.b;
             if (b != cur_b) {
                 if (cur_b >= 0) { flush(span); ++span; }
+                tic = 0; first_drain = true;
                 float* pose = sPose + (span & 1) * 16;
                 float* Wsm = sW + (span & 1) * TC_K;
                 if (g == 0) {
@@ -242,29 +320,42 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             }
             const float* pose = sPose + (span & 1) * 16;
             const unsigned char* As = base + SM::off_A + s * TC_STAGE_A;
-            unsigned char* Rs = base + SM::off_R + s * TC_STAGE_R;
+            if (tic == 0) ++chain;
+            // lazy drain of the previous hi chain, half a chain later (its MMAs completed long ago: no stall)
+            if (tic == TC_CHAIN / 2 && next_drain < chain) {
+                drain_hi(next_drain, prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats);
+                ++next_drain;
+            }
+            if (++tic == TC_CHAIN) tic = 0;
 
             mbar_wait(&fullB[s], ph);
 
-            // ---------------------------------------------------------------- gather: 4 x (2 pixels per warp)
-#pragma unroll 1
+            // ---------------------------------------------------------------- (i) D~ - D = b . W for this warp's 8 pixels
+            float mydot = 0.f;
+#pragma unroll
             for (int i4 = 0; i4 < 4; ++i4) {
-                const int pl = i4 * 2 + hw;                      // pixel slot within this warp (0..7)
-                const int nl = g * 8 + pl;                       // pixel within the tile
-                const bool in_tile = nl < cnt;
+                const int nl = g * 8 + i4 * 2 + hw;
                 const uint32_t offA = blkA * 8192 + sw128_32b_off(nl, ccA);
                 const float4 b0 = *reinterpret_cast<const float4*>(As + offA);
                 const float4 b1 = *reinterpret_cast<const float4*>(As + offA + 2 * 8192);
                 float dot = b0.x * wreg[0] + b0.y * wreg[1] + b0.z * wreg[2] + b0.w * wreg[3]
                           + b1.x * wreg[4] + b1.y * wreg[5] + b1.z * wreg[6] + b1.w * wreg[7];
                 dot = hsum16(dot);
+                const float other = __shfl_sync(0xffffffffu, dot, 16);
+                if (lane == 2 * i4) mydot = dot;
+                if (lane == 2 * i4 + 1) mydot = other;
+            }
+            // ---------------------------------------------------------------- (ii) warp geometry, thread per pixel (bundlenet.py:208-224, :231)
+            if (lane < 8) {
+                int n; bool valid;
+                if (grid2d) { const int gx = tc.tx0 + lane, gy = tc.ty0 + g; valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
+                else { const int nl = g * 8 + lane; valid = nl < tc.cnt; n = tc.n0 + nl; }
                 float mask = 0.f, x = 0.f, y = 0.f, iZ = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, dx = 0.f, dy = 0.f;
                 int x0 = 0, y0 = 0;
-                if (in_tile) {
-                    const size_t gi = (size_t)b * N + n0 + nl;
-                    const float* pp = prm.p + (size_t)b * 3 * N + n0 + nl;
+                if (valid) {
+                    const float* pp = prm.p + (size_t)b * 3 * N + n;
                     const float p0 = __ldg(pp), p1 = __ldg(pp + N), p2 = __ldg(pp + 2 * (size_t)N);
-                    const float Dt = __ldg(prm.D + gi) + dot;                                   // bundlenet.py:208
+                    const float Dt = __ldg(prm.D + (size_t)b * N + n) + mydot;
                     rx = pose[0] * p0 + pose[1] * p1 + pose[2] * p2;
                     ry = pose[3] * p0 + pose[4] * p1 + pose[5] * p2;
                     rz = pose[6] * p0 + pose[7] * p1 + pose[8] * p2;
@@ -277,93 +368,116 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                         x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
                     }
                 }
-                float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
-                if (mask != 0.f) {
-                    const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
-                    const float* img = prm.conv2 + (size_t)b * h * w * c2;
-                    const float* c1 = prm.conv1 + ((size_t)b * N + n0 + nl) * C + 4 * hl;
-                    if constexpr (!FLY) {
-                        const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-                        const float* t00 = img + ((size_t)y0 * w + x0) * c2 + 4 * hl;
-                        const float* t01 = img + ((size_t)y0 * w + x1) * c2 + 4 * hl;
-                        const float* t10 = img + ((size_t)y1 * w + x0) * c2 + 4 * hl;
-                        const float* t11 = img + ((size_t)y1 * w + x1) * c2 + 4 * hl;
-#pragma unroll
-                        for (int j = 0; j < NCH; ++j) {
-                            const int co = 64 * j;
-                            const float4 f1 = ld_stream_f4(c1 + co);
-                            const float4 a00 = ldg4(t00 + co), a01 = ldg4(t01 + co), a10 = ldg4(t10 + co), a11 = ldg4(t11 + co);
-                            const float4 g00 = ldg4(t00 + C + co), g01 = ldg4(t01 + C + co), g10 = ldg4(t10 + C + co), g11 = ldg4(t11 + C + co);
-                            const float4 e00 = ldg4(t00 + 2 * C + co), e01 = ldg4(t01 + 2 * C + co), e10 = ldg4(t10 + 2 * C + co), e11 = ldg4(t11 + 2 * C + co);
-#define BANET_CH(F)                                                                                              \
-                            {                                                                                    \
-                                const float f2 = w00 * a00.F + w01 * a01.F + w10 * a10.F + w11 * a11.F;          \
-                                const float gx = w00 * g00.F + w01 * g01.F + w10 * g10.F + w11 * g11.F;          \
-                                const float gy = w00 * e00.F + w01 * e01.F + w10 * e10.F + w11 * e11.F;          \
-                                const float d = f1.F - f2;                                                       \
-                                m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);       \
-                                q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                      \
-                                rb[4 * j + ci] += fabsf(d); ++ci;                                                \
-                            }
-                            int ci = 0;
-                            BANET_CH(x) BANET_CH(y) BANET_CH(z) BANET_CH(w)
-#undef BANET_CH
-                        }
-                    } else {
-                        // F2-only map: central differences with REFLECT-by-one borders (bundlenet.py:92-100) folded into the
-                        // bilinear blend: 12 texels = rows y0,Y1 x columns XM,x0,X1,XP  +  rows YM,YP x columns x0,X1
-                        const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
-                        const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
-                        const float* r0 = img + (size_t)y0 * w * c2 + 4 * hl;
-                        const float* r1 = img + (size_t)Y1 * w * c2 + 4 * hl;
-                        const float* rm = img + (size_t)YM * w * c2 + 4 * hl;
-                        const float* rp = img + (size_t)YP * w * c2 + 4 * hl;
-                        const size_t oM = (size_t)XM * c2, o0 = (size_t)x0 * c2, o1 = (size_t)X1 * c2, oP = (size_t)XP * c2;
-                        const float h00 = 0.5f * w00, h01 = 0.5f * w01, h10 = 0.5f * w10, h11 = 0.5f * w11;
-#pragma unroll
-                        for (int j = 0; j < NCH; ++j) {
-                            const int co = 64 * j;
-                            const float4 f1 = ld_stream_f4(c1 + co);
-                            const float4 aM0 = ldg4(r0 + oM + co), a00 = ldg4(r0 + o0 + co), a10 = ldg4(r0 + o1 + co), aP0 = ldg4(r0 + oP + co);
-                            const float4 aM1 = ldg4(r1 + oM + co), a01 = ldg4(r1 + o0 + co), a11 = ldg4(r1 + o1 + co), aP1 = ldg4(r1 + oP + co);
-                            const float4 a0m = ldg4(rm + o0 + co), a1m = ldg4(rm + o1 + co), a0p = ldg4(rp + o0 + co), a1p = ldg4(rp + o1 + co);
-                            // naming: aXY = F[column X in {M,0,1,P}][row Y in {m,0,1,p}]
-#define BANET_CH(F)                                                                                              \
-                            {                                                                                    \
-                                const float f2 = w00 * a00.F + w01 * a10.F + w10 * a01.F + w11 * a11.F;          \
-                                const float gx = h00 * (a10.F - aM0.F) + h01 * (aP0.F - a00.F)                   \
-                                               + h10 * (a11.F - aM1.F) + h11 * (aP1.F - a01.F);                  \
-                                const float gy = h00 * (a01.F - a0m.F) + h10 * (a0p.F - a00.F)                   \
-                                               + h01 * (a11.F - a1m.F) + h11 * (a1p.F - a10.F);                  \
-                                const float d = f1.F - f2;                                                       \
-                                m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);       \
-                                q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                      \
-                                rb[4 * j + ci] += fabsf(d); ++ci;                                                \
-                            }
-                            int ci = 0;
-                            BANET_CH(x) BANET_CH(y) BANET_CH(z) BANET_CH(w)
-#undef BANET_CH
-                        }
-                    }
-                }
-                m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
-                if (hl == 0) {
-                    float4* rp4 = reinterpret_cast<float4*>(myRec + pl * TC_REC);
-                    rp4[0] = make_float4(m11, m12, m22, q1);
-                    rp4[1] = make_float4(q2, x, y, iZ);
-                    rp4[2] = make_float4(rx, ry, rz, mask);
-                }
+                float4* r4 = reinterpret_cast<float4*>(myRec + lane * TC_REC);
+                r4[0] = make_float4(__int_as_float(x0), __int_as_float(y0), dx, dy);
+                r4[1] = make_float4(mask, x, y, iZ);
+                r4[2] = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
             }
             __syncwarp();
 
-            // ---------------------------------------------------------------- per-pixel 2x7 algebra (lanes 0..7), bundlenet.py:49-74
+            // ---------------------------------------------------------------- (iii) gather: 8 units = 4 pixel pairs x NCH... (unit = pair, 64-channel chunk)
+            constexpr int NUNIT = 4 * NCH;
+            float4 tb[3][13];
+            float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
+            const float* img = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl;
+
+            auto issue = [&](int u, float4* t) {
+                const int pl = 2 * (u / NCH) + hw, co = 64 * (u % NCH);
+                const float4 ra = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
+                const float4 rq = *reinterpret_cast<const float4*>(myRec + pl * TC_REC + 4);
+                if (rq.x != 0.f) {
+                    const int x0 = __float_as_int(ra.x), y0 = __float_as_int(ra.y);
+                    const int n = __float_as_int(myRec[pl * TC_REC + 11]);
+                    t[0] = ld_stream_f4(prm.conv1 + ((size_t)b * N + n) * C + 4 * hl + co);
+                    if constexpr (!FLY) {
+                        const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+                        const float* t00 = img + ((size_t)y0 * w + x0) * c2 + co;
+                        const float* t01 = img + ((size_t)y0 * w + x1) * c2 + co;
+                        const float* t10 = img + ((size_t)y1 * w + x0) * c2 + co;
+                        const float* t11 = img + ((size_t)y1 * w + x1) * c2 + co;
+                        t[1] = ldg4(t00); t[2] = ldg4(t01); t[3] = ldg4(t10); t[4] = ldg4(t11);
+                        t[5] = ldg4(t00 + C); t[6] = ldg4(t01 + C); t[7] = ldg4(t10 + C); t[8] = ldg4(t11 + C);
+                        t[9] = ldg4(t00 + 2 * C); t[10] = ldg4(t01 + 2 * C); t[11] = ldg4(t10 + 2 * C); t[12] = ldg4(t11 + 2 * C);
+                    } else {
+                        // F2-only map: 12 texels = rows y0,Y1 x columns XM,x0,X1,XP  +  rows YM,YP x columns x0,X1 (REFLECT-by-one, bundlenet.py:97)
+                        const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
+                        const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
+                        const float* r0 = img + (size_t)y0 * w * c2 + co;
+                        const float* r1 = img + (size_t)Y1 * w * c2 + co;
+                        const float* rm = img + (size_t)YM * w * c2 + co;
+                        const float* rp = img + (size_t)YP * w * c2 + co;
+                        const size_t oM = (size_t)XM * c2, o0 = (size_t)x0 * c2, o1 = (size_t)X1 * c2, oP = (size_t)XP * c2;
+                        t[1] = ldg4(r0 + oM); t[2] = ldg4(r0 + o0); t[3] = ldg4(r0 + o1); t[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
+                        t[5] = ldg4(r1 + oM); t[6] = ldg4(r1 + o0); t[7] = ldg4(r1 + o1); t[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
+                        t[9] = ldg4(rm + o0); t[10] = ldg4(rm + o1); t[11] = ldg4(rp + o0); t[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
+                    }
+                }
+            };
+            auto compute = [&](int u, const float4* t) {
+                const int pl = 2 * (u / NCH) + hw, j = u % NCH;
+                const float4 ra = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
+                const float mask = myRec[pl * TC_REC + 4];
+                if (j == 0) { m11 = m12 = m22 = q1 = q2 = 0.f; }
+                if (mask != 0.f) {
+                    const float dx = ra.z, dy = ra.w;
+                    const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+                    if constexpr (!FLY) {
+#define BANET_CH(F, CI)                                                                                              \
+                        {                                                                                            \
+                            const float f2 = w00 * t[1].F + w01 * t[2].F + w10 * t[3].F + w11 * t[4].F;              \
+                            const float gx = w00 * t[5].F + w01 * t[6].F + w10 * t[7].F + w11 * t[8].F;              \
+                            const float gy = w00 * t[9].F + w01 * t[10].F + w10 * t[11].F + w11 * t[12].F;           \
+                            const float d = t[0].F - f2;                                                             \
+                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
+                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
+                            rb[4 * j + CI] += fabsf(d);                                                              \
+                        }
+                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                    } else {
+                        const float h00 = 0.5f * w00, h01 = 0.5f * w01, h10 = 0.5f * w10, h11 = 0.5f * w11;
+                        // t: 1 aM0, 2 a00, 3 a10, 4 aP0, 5 aM1, 6 a01, 7 a11, 8 aP1, 9 a0m, 10 a1m, 11 a0p, 12 a1p  (aXY: column X, row Y)
+#define BANET_CH(F, CI)                                                                                              \
+                        {                                                                                            \
+                            const float f2 = w00 * t[2].F + w01 * t[3].F + w10 * t[6].F + w11 * t[7].F;              \
+                            const float gx = h00 * (t[3].F - t[1].F) + h01 * (t[4].F - t[2].F)                       \
+                                           + h10 * (t[7].F - t[5].F) + h11 * (t[8].F - t[6].F);                      \
+                            const float gy = h00 * (t[6].F - t[9].F) + h10 * (t[11].F - t[2].F)                      \
+                                           + h01 * (t[7].F - t[10].F) + h11 * (t[12].F - t[3].F);                    \
+                            const float d = t[0].F - f2;                                                             \
+                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
+                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
+                            rb[4 * j + CI] += fabsf(d);                                                              \
+                        }
+                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                    }
+                }
+                if (j == NCH - 1) {
+                    m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
+                    if (hl == 0) {      // overwrite (x0,y0,dx,dy) and n of this pixel's record: no longer needed
+                        *reinterpret_cast<float4*>(myRec + pl * TC_REC) = make_float4(m11, m12, m22, q1);
+                        myRec[pl * TC_REC + 11] = q2;
+                    }
+                }
+            };
+            issue(0, tb[0]);
+            issue(1, tb[1]);
+#pragma unroll
+            for (int u = 0; u < NUNIT; ++u) {
+                if (u + 2 < NUNIT) issue(u + 2, tb[(u + 2) % 3]);
+                compute(u, tb[u % 3]);
+            }
+            __syncwarp();
+
+            // ---------------------------------------------------------------- (iv) per-pixel 2x7 algebra (lanes 0..7), bundlenet.py:49-74
             if (lane < 8) {
                 float* rec = myRec + lane * TC_REC;
                 const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
                              rc = *reinterpret_cast<const float4*>(rec + 8);
                 float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (rc.w != 0.f) {
-                    const float m11 = ra.x, m12 = ra.y, m22 = ra.z, q1 = ra.w, q2 = rbq.x, x = rbq.y, y = rbq.z, iZ = rbq.w;
+                if (rbq.x != 0.f) {
+                    const float m11 = ra.x, m12 = ra.y, m22 = ra.z, q1 = ra.w, q2 = rc.w, x = rbq.y, y = rbq.z, iZ = rbq.w;
                     const float rx = rc.x, ry = rc.y, rz = rc.z;
                     const float fx = pose[12], fy = pose[13];
                     const float a0[6] = {-fx * (x * y), -fx * (-1.f - x * x), -fx * y, -fx * (-iZ), 0.f, -fx * (x * iZ)};
@@ -391,7 +505,8 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             }
             __syncwarp();
 
-            // ---------------------------------------------------------------- R rows (and A_lo) for this warp's 8 pixels
+            // ---------------------------------------------------------------- (v) R rows (A_lo, R_lo) for this warp's 8 pixels
+            if (it > 0) mbar_wait(rfree, (it - 1) & 1);          // the previous tile's MMAs no longer read R / A_lo / R_lo
 #pragma unroll 2
             for (int i4 = 0; i4 < 4; ++i4) {
                 const int pl = i4 * 2 + hw, nl = g * 8 + pl;
@@ -401,26 +516,41 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                 const uint32_t offA = blkA * 8192 + sw128_32b_off(nl, ccA);
                 const float4 b0 = *reinterpret_cast<const float4*>(As + offA);
                 const float4 b1 = *reinterpret_cast<const float4*>(As + offA + 2 * 8192);
-                *reinterpret_cast<float4*>(Rs + offA) = make_float4(tf32_rna(sn * b0.x), tf32_rna(sn * b0.y), tf32_rna(sn * b0.z), tf32_rna(sn * b0.w));
-                *reinterpret_cast<float4*>(Rs + offA + 2 * 8192) = make_float4(tf32_rna(sn * b1.x), tf32_rna(sn * b1.y), tf32_rna(sn * b1.z), tf32_rna(sn * b1.w));
-                if constexpr (MODE == 2) {
-                    unsigned char* Al = base + SM::off_Alo + s * TC_STAGE_A;
+                const float4 p0 = make_float4(sn * b0.x, sn * b0.y, sn * b0.z, sn * b0.w);
+                const float4 p1 = make_float4(sn * b1.x, sn * b1.y, sn * b1.z, sn * b1.w);
+                const float4 h0 = make_float4(tf32_rna(p0.x), tf32_rna(p0.y), tf32_rna(p0.z), tf32_rna(p0.w));
+                const float4 h1 = make_float4(tf32_rna(p1.x), tf32_rna(p1.y), tf32_rna(p1.z), tf32_rna(p1.w));
+                *reinterpret_cast<float4*>(Rs + offA) = h0;
+                *reinterpret_cast<float4*>(Rs + offA + 2 * 8192) = h1;
+                if constexpr (MODE >= 2) {
+                    unsigned char* Al = base + SM::off_Alo;
                     *reinterpret_cast<float4*>(Al + offA) = make_float4(b0.x - tf32_trunc(b0.x), b0.y - tf32_trunc(b0.y), b0.z - tf32_trunc(b0.z), b0.w - tf32_trunc(b0.w));
                     *reinterpret_cast<float4*>(Al + offA + 2 * 8192) = make_float4(b1.x - tf32_trunc(b1.x), b1.y - tf32_trunc(b1.y), b1.z - tf32_trunc(b1.z), b1.w - tf32_trunc(b1.w));
                 }
-                if (hl == 0) *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 0)) = make_float4(tf32_rna(e0.x), tf32_rna(e0.y), tf32_rna(e0.z), tf32_rna(e0.w));
-                if (hl == 1) *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 1)) = make_float4(tf32_rna(e1.x), tf32_rna(e1.y), tf32_rna(e1.z), 0.f);
+                if constexpr (MODE == 3) {
+                    unsigned char* Rl = base + SM::off_Rlo;
+                    *reinterpret_cast<float4*>(Rl + offA) = make_float4(p0.x - h0.x, p0.y - h0.y, p0.z - h0.z, p0.w - h0.w);
+                    *reinterpret_cast<float4*>(Rl + offA + 2 * 8192) = make_float4(p1.x - h1.x, p1.y - h1.y, p1.z - h1.z, p1.w - h1.w);
+                }
+                if (hl < 2) {
+                    const float4 ev = hl == 0 ? e0 : make_float4(e1.x, e1.y, e1.z, 0.f);
+                    const float4 eh = make_float4(tf32_rna(ev.x), tf32_rna(ev.y), tf32_rna(ev.z), tf32_rna(ev.w));
+                    const uint32_t offE = 4 * 8192 + sw128_32b_off(nl, hl);
+                    *reinterpret_cast<float4*>(Rs + offE) = eh;
+                    if constexpr (MODE == 3)
+                        *reinterpret_cast<float4*>(base + SM::off_Rlo + offE) = make_float4(ev.x - eh.x, ev.y - eh.y, ev.z - eh.z, ev.w - eh.w);
+                }
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ready[s]);
+            if (lane == 0) mbar_arrive(ready);
         }
         if (cur_b >= 0) flush(span);
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if (warp == 0) tmem_dealloc<TC_TMEM_COLS>(tmem);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -434,7 +564,8 @@ bool tc_supported(const banet_level_t* lv)
 int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan)
 {
     plan->KP = TC_K;
-    plan->tiles_per_pair = (lv->N + TC_TILE - 1) / TC_TILE;
+    if (lv->grid_w > 0) plan->tiles_per_pair = ((lv->grid_w + 7) / 8) * ((lv->grid_h + 7) / 8);
+    else plan->tiles_per_pair = (lv->N + TC_TILE - 1) / TC_TILE;
     plan->total_tiles = (long long)lv->nb * plan->tiles_per_pair;
     long long grid = num_sms;
     if (grid > plan->total_tiles) grid = plan->total_tiles;
@@ -460,13 +591,23 @@ static int launch_tc(const CUtensorMap& tm, const BuildParams& prm, int grid, cu
     return BANET_OK;
 }
 
+template <int NCH, bool FLY>
+static int launch_tc_mode(int mode, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+{
+    if (mode == 1) return launch_tc<NCH, FLY, 1>(tm, prm, grid, st);
+    if (mode == 2) return launch_tc<NCH, FLY, 2>(tm, prm, grid, st);
+    return launch_tc<NCH, FLY, 3>(tm, prm, grid, st);
+}
+
 int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const float* R, const float* T, const float* W,
                 float* H, float* g, float* rbar_sum, float* nvalid, void* ws, cudaStream_t st)
 {
     BANET_REQUIRE(tc_supported(lv), BANET_ERR_UNSUPPORTED,
                   "lm_build (tensor-core path) needs K=128, C in {64,128}, 16-B aligned tensors; got K=%d C=%d", lv->K, lv->C);
     CUtensorMap tm;
-    int rc = make_tmap_f32_2d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->N, TC_K, TC_TILE, 32);
+    int rc;
+    if (lv->grid_w > 0) rc = make_tmap_f32_3d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->grid_h, lv->grid_w, TC_K, 8, 8, 32);
+    else rc = make_tmap_f32_2d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->N, TC_K, TC_TILE, 32);
     if (rc) return rc;
     BuildParams prm;
     prm.nb = lv->nb; prm.N = lv->N; prm.C = lv->C; prm.K = lv->K; prm.h = lv->h; prm.w = lv->w; prm.c2 = lv->conv2_channels;
@@ -475,13 +616,12 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.partials = reinterpret_cast<float*>(ws);
     prm.slot_floats = plan.slot_floats; prm.max_span = plan.max_span;
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
+    prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h; prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0;
+    prm.hdd_transposed = 1;
     const bool fly = lv->conv2_channels == lv->C;
     const int nch = lv->C / 64;
-#define BANET_TC(NCHV, FLYV)                                                                        \
-    rc = (mode == 2) ? launch_tc<NCHV, FLYV, 2>(tm, prm, plan.grid, st) : launch_tc<NCHV, FLYV, 1>(tm, prm, plan.grid, st)
-    if (nch == 2) { if (fly) BANET_TC(2, true); else BANET_TC(2, false); }
-    else          { if (fly) BANET_TC(1, true); else BANET_TC(1, false); }
-#undef BANET_TC
+    if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, prm, plan.grid, st);
+    else          rc = fly ? launch_tc_mode<1, true>(mode, tm, prm, plan.grid, st) : launch_tc_mode<1, false>(mode, tm, prm, plan.grid, st);
     if (rc) return rc;
     return launch_lm_reduce(prm, plan.grid, H, g, rbar_sum, nvalid, st);
 }

@@ -12,7 +12,7 @@ using namespace tc;
 constexpr int ST_PX = 64, ST_M = 128, ST_N = 160;
 
 __global__ void __launch_bounds__(128, 1)
-tc_selftest_kernel(const __grid_constant__ CUtensorMap tmapA, const float* __restrict__ Rg, float* __restrict__ Dg, int mode, int use_rna)
+tc_selftest_kernel(const __grid_constant__ CUtensorMap tmapA, const float* __restrict__ Rg, float* __restrict__ Dg, int mode, int use_rna, int repeat)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -58,6 +58,7 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmapA, const float* __res
         tc_fence_after_sync();
         constexpr uint32_t idesc = make_idesc_tf32_mn_mn(ST_M, ST_N);
         uint32_t acc = 0;
+        for (int rep = 0; rep < repeat; ++rep)
         for (int pass = 0; pass <= mode; ++pass) {
             const uint32_t a0 = smem_u32(pass ? sAlo : sA), b0 = smem_u32(sR);
             for (int kk = 0; kk < ST_PX / 8; ++kk) {
@@ -88,7 +89,7 @@ tc_selftest_kernel(const __grid_constant__ CUtensorMap tmapA, const float* __res
 
 using namespace banet;
 
-extern "C" int banet_tc_selftest(const float* A, const float* R, float* D, int mode, int use_rna, banet_stream_t stream)
+extern "C" int banet_tc_selftest(const float* A, const float* R, float* D, int mode, int use_rna, int repeat, banet_stream_t stream)
 {
     BANET_REQUIRE(A && R && D, BANET_ERR_BAD_ARG, "tc_selftest: null pointer");
     CUtensorMap tm;
@@ -97,7 +98,7 @@ extern "C" int banet_tc_selftest(const float* A, const float* R, float* D, int m
     const size_t smem = 65536 + 40960 + 1024;
     cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("tc_selftest smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-    tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tm, R, D, mode, use_rna);
+    tc_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tm, R, D, mode, use_rna, repeat < 1 ? 1 : repeat);
     BANET_CUDA_LAUNCH_CHECK("tc_selftest_kernel launch");
     return BANET_OK;
 }

@@ -145,6 +145,7 @@ class Level:
     p: Tensor                 # [nb,3,N]
     D: Tensor                 # [nb,N,1]
     B: Optional[Tensor]       # [nb,N,K] or None
+    grid: Optional[Tuple[int, int]] = None   # (grid_w, grid_h) if the N points are a row-major raster grid (locality hint)
 
     def as_struct(self) -> Tuple[BanetLevel, list]:
         conv1 = _chk(self.conv1, "conv1"); nb, N, Cc = conv1.shape
@@ -157,8 +158,11 @@ class Level:
         if conv2.shape[0] != nb:
             raise _lib.BanetError("conv2 batch mismatch")
         keep = [conv1, conv2, intr, p, D, B]
+        gw, gh = (0, 0) if self.grid is None else self.grid
+        if gw * gh not in (0, N):
+            raise _lib.BanetError(f"grid {gw}x{gh} does not match N={N}")
         return BanetLevel(nb, N, Cc, K, h, w, c2, conv1.data_ptr(), conv2.data_ptr(), intr.data_ptr(), p.data_ptr(),
-                          D.data_ptr(), _ptr(B)), keep
+                          D.data_ptr(), _ptr(B), gw, gh), keep
 
 
 def lm_build(level: Level, R: Tensor, T: Tensor, W: Optional[Tensor], precision: int = _lib.PREC_FP32_SIMT):

@@ -90,6 +90,7 @@ class SceneLevel:
     D: torch.Tensor            # [nb,N,1]
     B: Optional[torch.Tensor]  # [nb,N,K]
     points: torch.Tensor       # [nb,N,2] level-pixel coordinates
+    grid: Optional[tuple] = None   # (w,h) when the points are the dense row-major pixel grid
 
     @property
     def N(self):
@@ -178,5 +179,5 @@ def make_scene(nb: int, H: int, W: int, C: int, K: int, level_ids=(0, 1, 2, 3), 
             px = fx[b0:b1] * (X[:, 0] / X[:, 2]) + ox[b0:b1]
             py = fy[b0:b1] * (X[:, 1] / X[:, 2]) + oy[b0:b1]
             conv1[b0:b1] = bilinear_zero_pad(f2, px, py)
-        levels.append(SceneLevel(lid, h, w, conv1, conv2, intr, p.contiguous(), D, Bm, pts))
+        levels.append(SceneLevel(lid, h, w, conv1, conv2, intr, p.contiguous(), D, Bm, pts, (w, h) if n_points is None else None))
     return Scene(levels, R_true, T_true, W_true, R0, T0, W0)

@@ -90,12 +90,16 @@ typedef struct banet_level {
     const float* p;           /* [nb,3,N]      :358 */
     const float* D;           /* [nb,N,1]      :343 */
     const float* B;           /* [nb,N,K] or NULL  :344 */
+    int grid_w, grid_h;       /* locality hint, results do not depend on it: 0,0 = unstructured point list; otherwise the N points
+                                 are the row-major raster grid x<grid_w, y<grid_h (N == grid_w*grid_h) and the kernels walk it in
+                                 8x8 tiles so that every conv2 texel is fetched from HBM about once */
 } banet_level_t;
 
-#define BANET_PREC_AUTO    (-1)   /* TF32X2 where the tensor-core path applies (K=128, C in {64,128}), else FP32_SIMT */
+#define BANET_PREC_AUTO    (-1)   /* TF32X3 where the tensor-core path applies (K=128, C in {64,128}), else FP32_SIMT */
 #define BANET_PREC_FP32_SIMT 0   /* every contraction in fp32 FFMA (reference-exact arithmetic type)   */
 #define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32: basis truncated by the tensor core, s*b rounded to nearest */
 #define BANET_PREC_TF32X2    2   /* split-A two-pass tf32: b = trunc(b) + (b - trunc(b)); only s*b's rounding remains             */
+#define BANET_PREC_TF32X3    3   /* three passes: also s*b = hi + lo; the dropped lo*lo term is ~2^-22: fp32-grade sums          */
 
 /* Normal equations + damping statistics of one iteration (bundlenet.py:206-239, 259-263 and the
  * mean-|diff| of :243), fused: J, G, d are never materialised.
@@ -152,8 +156,9 @@ int banet_depth_compose(const float* init_depth, const float* basis, const float
 
 /* Diagnostic (not part of the reference's interface): one 64-pixel k-tile through the TMA + tcgen05 building
  * blocks of the tensor-core build path.  A [64,128], R [64,160] -> D [128,160] = A^T R.
- * mode 0: single tf32 pass; mode 1: split-A two-pass.  use_rna: round R to tf32 (nearest) first. */
-int banet_tc_selftest(const float* A, const float* R, float* D, int mode, int use_rna, banet_stream_t stream);
+ * mode 0: single tf32 pass; mode 1: split-A two-pass.  use_rna: round R to tf32 (nearest) first.
+ * repeat: accumulate the same tile `repeat` times into TMEM (probes the accumulator's rounding). */
+int banet_tc_selftest(const float* A, const float* R, float* D, int mode, int use_rna, int repeat, banet_stream_t stream);
 
 #ifdef __cplusplus
 }

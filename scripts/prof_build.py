@@ -6,7 +6,7 @@ prec = int(os.environ.get("BANET_PREC", "2")); fly = int(os.environ.get("BANET_F
 sc = synth.make_scene(nb=nb, H=480, W=640, C=128, K=128, level_ids=(3,), seed=5, device="cuda", dtype=torch.float32)
 lv = sc.levels[0]
 conv2 = lv.conv2[..., :128].contiguous() if fly else lv.conv2
-L = ops.Level(lv.conv1, conv2, lv.intr, lv.p, lv.D, lv.B)
+L = ops.Level(lv.conv1, conv2, lv.intr, lv.p, lv.D, lv.B, grid=lv.grid if int(os.environ.get("BANET_GRID", "1")) else None)
 for _ in range(int(os.environ.get("BANET_REPS", "3"))):
     ops.lm_build(L, sc.R0, sc.T0, sc.W0, precision=prec)
 torch.cuda.synchronize()

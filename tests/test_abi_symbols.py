@@ -34,10 +34,10 @@ def test_version_and_error_paths_without_gpu():
     rc = lib.banet_eqc_fwd(None, None, None, 1, 1, 1, 1, None, None, None, 0, None)
     assert rc == -1 and b"null" in lib.banet_last_error()
     assert lib.banet_eqc_workspace_bytes(2, 4096, 128, 134) > 0
-    lv = _lib.BanetLevel(32, 307200, 128, 128, 480, 640, 384, 1, 1, 1, 1, 1, 1)
+    lv = _lib.BanetLevel(32, 307200, 128, 128, 480, 640, 384, 1, 1, 1, 1, 1, 1, 0, 0)
     ws = lib.banet_lm_build_workspace_bytes(ctypes.byref(lv), 0)
     assert 0 < ws < (1 << 30)
-    lv_bad = _lib.BanetLevel(32, 307200, 128, 128, 480, 640, 100, 1, 1, 1, 1, 1, 1)
+    lv_bad = _lib.BanetLevel(32, 307200, 128, 128, 480, 640, 100, 1, 1, 1, 1, 1, 1, 0, 0)
     rc = lib.banet_lm_build(ctypes.byref(lv_bad), None, None, None, 0, None, None, None, None, None, 0, None)
     assert rc == -1 and b"conv2_channels" in lib.banet_last_error()
 
