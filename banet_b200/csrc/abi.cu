@@ -39,7 +39,7 @@ static int check_level(const banet_level_t* lv, const char* who)
 
 int resolve_precision(const banet_level_t* lv, int precision)
 {
-    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X3 : BANET_PREC_FP32_SIMT;
+    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X2 : BANET_PREC_FP32_SIMT;
     if (precision == BANET_PREC_FP32_SIMT) return precision;
     if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2 || precision == BANET_PREC_TF32X3) {
         if (!tc_supported(lv)) {

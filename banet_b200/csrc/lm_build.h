@@ -11,7 +11,8 @@ struct BuildParams {
     int slot_floats, max_span, tiles_per_pair;
     long long total_tiles;
     int grid_w, grid_h, tiles_x;      // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
-    int hdd_transposed;               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
+    int hdd_transposed;
+    long long* trace;                 // optional debug timeline buffer (NULL in production)               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
 };
 
 struct BuildPlan {

@@ -26,7 +26,9 @@
 // Warp roles (384 threads = 3 warpgroups, 1 CTA / SM, persistent over a contiguous tile range):
 //   warp 0     TMA producer: basis tile -> smem stage (2 stages, mbarrier complete_tx)          } warpgroup 0 gives its
 //   warp 1     MMA issuer (one thread): 8 tcgen05.mma per pass and tile; tcgen05.commit         } registers away
-//   warps 2-3  idle                                                                            } (setmaxnreg.dec 40)
+//   warp 2     L2 prefetcher, two tiles ahead: conv1 / p / D rows of the tile and (dense grid) the conv2 footprint the   } (setmaxnreg.dec 32)
+//              tile will sample, predicted from the flow of the tile just finished (cp.async.bulk.prefetch[.tensor])
+//   warp 3     idle
 //   warps 4-11 gather warps (setmaxnreg.inc 232), 8 pixels each per tile: D~ = D + b.W from the staged tile, thread-per-pixel warp geometry,
 //             then half-warp per pixel / lanes over channels for the 4-tap (or 12-texel, F2-only) gather with the loads of
 //             the next two (pixel pair, channel chunk) units in flight while the current one is reduced; per-pixel 2x7
@@ -35,15 +37,16 @@
 #include "lm_build.h"
 #include "tc_utils.cuh"
 #include "tmap.h"
+#include <stdlib.h>
+#include <limits.h>
 
 namespace banet {
 using namespace tc;
 
 constexpr int TC_TILE = 64;
-constexpr int TC_GW = 8;
-constexpr int TC_GW0 = 4;                          // first gather warp (warpgroup 1)
-constexpr int TC_THREADS = (TC_GW0 + TC_GW) * 32;  // 384
-constexpr int TC_CHAIN = 4;                        // tiles per hi-accumulator chain
+constexpr int TC_GW0 = 4;                          // first gather warp (warpgroup 1); warps 0-3 = producer, MMA issuer, 2 idle
+constexpr int TC_GWMAX = 16;                       // gather warps: 8 (8 pixels each, 3 load units in flight) or 16 (4 pixels, 1 unit)
+constexpr int TC_CHAIN = 8;                        // tiles per hi-accumulator chain (64 accumulation steps: ~ -1.6e-6 relative bias)
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_ACCL = 320;                       // TMEM column of the lo accumulator (hi: 0 and 160)
 constexpr int TC_K = 128;
@@ -62,15 +65,19 @@ template <int MODE> struct TcSmem {
     static constexpr int off_tmem = off_bar + 96;
     static constexpr int off_pose = off_misc + 128;                   // [2][16] floats
     static constexpr int off_W = off_pose + 128;                      // [2][128] floats
-    static constexpr int off_rec = off_W + 1024;                      // [GW][8][TC_REC] floats
-    static constexpr int off_cc = off_rec + TC_GW * 8 * TC_REC * 4;   // [GW][8][28] floats
-    static constexpr int total = off_cc + TC_GW * 8 * 28 * 4;
+    static constexpr int off_rec = off_W + 1024;                      // [64 pixels][TC_REC] floats
+    static constexpr int off_cc = off_rec + TC_TILE * TC_REC * 4;     // [64 pixel slots][28] floats
+    static constexpr int off_bb = off_cc + TC_TILE * 28 * 4;          // [2][TC_GWMAX][4] ints: tap-origin bounding boxes
+    static constexpr int total = off_bb + 2 * TC_GWMAX * 4 * 4;
     static constexpr int bytes = total + 1024;                        // slack for manual 1024-B alignment
 };
 
-__device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory"); }
 __device__ __forceinline__ int reflect_i(int i, int n) { i = i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); return i < 0 ? 0 : i; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define TC_TRACE(slot) do { if (prm.trace && blockIdx.x == 1 && lane == 0 && (g == 0 || g == GW - 1) && it >= 16 && it < 48) \
+        prm.trace[(((g == 0 ? 0 : 1) * 32 + (it - 16)) * 8) + (slot)] = gtime(); } while (0)
 __device__ __forceinline__ float hsum16(float v) {            // sum over the 16 lanes of a half-warp
     v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -88,9 +95,9 @@ __device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long lon
     return tc;
 }
 
-template <int NCH, bool FLY, int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams prm)
+template <int NCH, bool FLY, int MODE, int GW>
+__global__ void __launch_bounds__((TC_GW0 + GW) * 32, 1)
+lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapC2, const BuildParams prm)
 {
     using SM = TcSmem<MODE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -109,7 +116,12 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
     float* sW = reinterpret_cast<float*>(base + SM::off_W);
     float* sRec = reinterpret_cast<float*>(base + SM::off_rec);
     float* sCC = reinterpret_cast<float*>(base + SM::off_cc);
+    int* sBB = reinterpret_cast<int*>(base + SM::off_bb);
 
+    constexpr int TC_THREADS = (TC_GW0 + GW) * 32;
+    constexpr int PXW = TC_TILE / GW;                 // pixels per gather warp and tile (8 or 4)
+    constexpr int DEPTH = (GW == 8) ? 3 : 1;          // (pixel pair, 64-channel chunk) load units in flight per warp
+    constexpr int GREG = (GW == 8) ? 232 : 112;       // registers per gather thread after setmaxnreg
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = prm.N, h = prm.h, w = prm.w, c2 = prm.c2;
     const bool grid2d = prm.grid_w > 0;
@@ -120,10 +132,10 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
     if (tid == 0) {
         mbar_init(&fullB[0], 1); mbar_init(&fullB[1], 1);
         mbar_init(&emptyB[0], 1); mbar_init(&emptyB[1], 1);
-        mbar_init(ready, TC_GW); mbar_init(rfree, 1);
-        mbar_init(flushb, 1); mbar_init(tmemfree, TC_GW);
+        mbar_init(ready, GW); mbar_init(rfree, 1);
+        mbar_init(flushb, 1); mbar_init(tmemfree, GW);
         mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1);
-        mbar_init(&drained[0], TC_GW); mbar_init(&drained[1], TC_GW);
+        mbar_init(&drained[0], GW); mbar_init(&drained[1], GW);
         fence_barrier_init();
         prefetch_tmap(&tmapB);
     }
@@ -141,7 +153,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
     const uint32_t tmem = *s_tmem;
 
     if (warp < TC_GW0) {
-      setmaxnreg_dec<40>();
+      setmaxnreg_dec<32>();
       if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
@@ -203,17 +215,63 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             }
             if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); }
         }
-      }     // warps 2,3 of warpgroup 0 idle
+      } else if (warp == 2) {
+        // ===================================================================== L2 prefetcher (whole warp), two tiles ahead
+        constexpr int PF_AHEAD = 2;
+        constexpr int PF_M = FLY ? 2 : 1;                 // margin left/top of the predicted tap origin
+        int it = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++it) {
+            const long long tp = t + PF_AHEAD;
+            if (tp >= t_end) break;
+            const TileCoord tc = tile_coord(prm, t), tn = tile_coord(prm, tp);
+            // streaming inputs of tile tp (addresses known exactly)
+            if (grid2d) {
+                if (lane < 8) {
+                    const int gy = tn.ty0 + lane;
+                    if (gy < prm.grid_h && tn.tx0 < prm.grid_w) {
+                        const size_t n = (size_t)gy * prm.grid_w + tn.tx0;
+                        const int wpx = min(8, prm.grid_w - tn.tx0);
+                        prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + n) * C, (uint32_t)(wpx * C * 4));
+                        if ((n & 3) == 0 && (N & 3) == 0) {
+                            const uint32_t by = (uint32_t)(((wpx * 4) + 15) & ~15);
+                            prefetch_l2_bulk(prm.D + (size_t)tn.b * N + n, by);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + n, by);
+                        }
+                    }
+                }
+            } else if (lane == 0) {
+                prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + tn.n0) * C, (uint32_t)(tn.cnt * C * 4));
+                if ((N & 3) == 0) {
+                    const uint32_t by = (uint32_t)(((tn.cnt * 4) + 15) & ~15);
+                    prefetch_l2_bulk(prm.D + (size_t)tn.b * N + tn.n0, by);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + tn.n0, by);
+                }
+            }
+            // conv2 footprint of tile tp, predicted from the flow of tile t (dense grid only)
+            if (grid2d) {
+                const bool have_bb = mbar_wait_bounded(ready, it & 1, 2000);   // tile t's geometry (and bounding boxes) complete
+                int xmn = INT_MAX, ymn = INT_MAX;
+                if (have_bb && lane < GW) { xmn = sBB[((it & 1) * TC_GWMAX + lane) * 4 + 0]; ymn = sBB[((it & 1) * TC_GWMAX + lane) * 4 + 2]; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { xmn = min(xmn, __shfl_xor_sync(0xffffffffu, xmn, o)); ymn = min(ymn, __shfl_xor_sync(0xffffffffu, ymn, o)); }
+                const int fx = (xmn == INT_MAX || tn.b != tc.b) ? 0 : xmn - tc.tx0;
+                const int fy = (ymn == INT_MAX || tn.b != tc.b) ? 0 : ymn - tc.ty0;
+                if (lane < c2 / C) prefetch_l2_tensor_4d(&tmapC2, lane * C, tn.tx0 + fx - PF_M, tn.ty0 + fy - PF_M, tn.b);
+            }
+        }
+      }     // warp 3 of warpgroup 0 idle
     } else {
         // ===================================================================== gather warps
-        setmaxnreg_inc<232>();
+        setmaxnreg_inc<GREG>();
         const int g = warp - TC_GW0, hw = lane >> 4, hl = lane & 15;
         const int gtid = tid - TC_GW0 * 32;
         const int blkA = hl >> 3, ccA = hl & 7;                 // this lane's two 16-B chunks of a 128-float row: blocks blkA and 2+blkA
         float wreg[8];
         float rb[NCH * 4];
-        float* myRec = sRec + g * 8 * TC_REC;
-        float* myCC = sCC + (g * 8 + (lane & 7)) * 28;
+        float* myRec = sRec + g * PXW * TC_REC;
+        float* myCC = sCC + (g * PXW + (lane & (PXW - 1))) * 28;
         const SlotLayout L{TC_K, C};
         unsigned char* Rs = base + SM::off_R;
         int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, next_drain = 0;
@@ -224,9 +282,11 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             const int q = warp & 3, row = q * 32 + lane;
             const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16) + col0;
             float v[32];
+            constexpr int NSUB = GW / 4;                 // warps per TMEM lane quadrant; they split the 4 H_dd column blocks
+            const int sub = g >> 2;
 #pragma unroll 1
-            for (int cbi = 0; cbi < 2; ++cbi) {
-                const int cb = (g >= 4 ? 2 : 0) + cbi;
+            for (int cbi = 0; cbi < 4 / NSUB; ++cbi) {
+                const int cb = sub * (4 / NSUB) + cbi;
                 tmem_ld_32x32(tq + cb * 32, v);
                 float* dst = slot + (size_t)(cb * 32) * TC_K + row;
                 if (overwrite) {
@@ -237,7 +297,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                     for (int j = 0; j < 32; ++j) dst[(size_t)j * TC_K] += v[j];
                 }
             }
-            if (g < 4) {
+            if (sub == 0) {
                 tmem_ld_32x32(tq + 128, v);
                 float* dst = slot + L.off_ext() + row;
 #pragma unroll
@@ -271,19 +331,19 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                 for (int j = 0; j < NCH; ++j)
                     *reinterpret_cast<float4*>(scratch + g * C + 64 * j + 4 * hl) = make_float4(rb[4 * j], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
             }
-            gather_bar();
+            gather_bar<GW * 32>();
             if (gtid < C) {
                 float s = 0.f;
 #pragma unroll
-                for (int wq = 0; wq < TC_GW; ++wq) s += scratch[wq * C + gtid];
+                for (int wq = 0; wq < GW; ++wq) s += scratch[wq * C + gtid];
                 slot[L.off_rbar() + gtid] = s;
             }
             if (gtid < 28) {
                 float s = 0.f;
-                for (int e = 0; e < TC_GW * 8; ++e) s += sCC[e * 28 + gtid];
+                for (int e = 0; e < TC_TILE; ++e) s += sCC[e * 28 + gtid];
                 slot[L.off_cc() + gtid] = s;
             }
-            gather_bar();
+            gather_bar<GW * 32>();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmemfree);
         };
@@ -303,14 +363,14 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                     else if (lane < 16) pose[lane] = prm.intr[b * 4 + lane - 12];
                     for (int k = lane; k < TC_K; k += 32) Wsm[k] = prm.W[b * TC_K + k];
                 }
-                gather_bar();
+                gather_bar<GW * 32>();
                 {
                     const float4 w0 = *reinterpret_cast<const float4*>(Wsm + blkA * 32 + ccA * 4);
                     const float4 w1 = *reinterpret_cast<const float4*>(Wsm + (2 + blkA) * 32 + ccA * 4);
                     wreg[0] = w0.x; wreg[1] = w0.y; wreg[2] = w0.z; wreg[3] = w0.w;
                     wreg[4] = w1.x; wreg[5] = w1.y; wreg[6] = w1.z; wreg[7] = w1.w;
                 }
-                if (lane < 8) {
+                if (lane < PXW) {
 #pragma unroll
                     for (int q = 0; q < 28; ++q) myCC[q] = 0.f;
                 }
@@ -320,6 +380,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             }
             const float* pose = sPose + (span & 1) * 16;
             const unsigned char* As = base + SM::off_A + s * TC_STAGE_A;
+            TC_TRACE(0);
             if (tic == 0) ++chain;
             // lazy drain of the previous hi chain, half a chain later (its MMAs completed long ago: no stall)
             if (tic == TC_CHAIN / 2 && next_drain < chain) {
@@ -328,13 +389,15 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             }
             if (++tic == TC_CHAIN) tic = 0;
 
+            TC_TRACE(1);
             mbar_wait(&fullB[s], ph);
+            TC_TRACE(2);
 
-            // ---------------------------------------------------------------- (i) D~ - D = b . W for this warp's 8 pixels
+            // ---------------------------------------------------------------- (i) D~ - D = b . W for this warp's PXW pixels
             float mydot = 0.f;
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-                const int nl = g * 8 + i4 * 2 + hw;
+            for (int i4 = 0; i4 < PXW / 2; ++i4) {
+                const int nl = g * PXW + i4 * 2 + hw;
                 const uint32_t offA = blkA * 8192 + sw128_32b_off(nl, ccA);
                 const float4 b0 = *reinterpret_cast<const float4*>(As + offA);
                 const float4 b1 = *reinterpret_cast<const float4*>(As + offA + 2 * 8192);
@@ -346,10 +409,11 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                 if (lane == 2 * i4 + 1) mydot = other;
             }
             // ---------------------------------------------------------------- (ii) warp geometry, thread per pixel (bundlenet.py:208-224, :231)
-            if (lane < 8) {
+            if (lane < PXW) {
                 int n; bool valid;
-                if (grid2d) { const int gx = tc.tx0 + lane, gy = tc.ty0 + g; valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
-                else { const int nl = g * 8 + lane; valid = nl < tc.cnt; n = tc.n0 + nl; }
+                const int nl = g * PXW + lane;
+                if (grid2d) { const int gx = tc.tx0 + (nl & 7), gy = tc.ty0 + (nl >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
+                else { valid = nl < tc.cnt; n = tc.n0 + nl; }
                 float mask = 0.f, x = 0.f, y = 0.f, iZ = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, dx = 0.f, dy = 0.f;
                 int x0 = 0, y0 = 0;
                 if (valid) {
@@ -368,16 +432,23 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                         x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
                     }
                 }
+                if (grid2d) {         // tap-origin bounding box of this warp's pixels, for the L2 prefetcher
+                    int bx = mask != 0.f ? x0 : INT_MAX, by = mask != 0.f ? y0 : INT_MAX;
+#pragma unroll
+                    for (int o = PXW / 2; o > 0; o >>= 1) { bx = min(bx, __shfl_xor_sync((1u << PXW) - 1u, bx, o)); by = min(by, __shfl_xor_sync((1u << PXW) - 1u, by, o)); }
+                    if (lane == 0) { sBB[((it & 1) * TC_GWMAX + g) * 4 + 0] = bx; sBB[((it & 1) * TC_GWMAX + g) * 4 + 2] = by; }
+                }
                 float4* r4 = reinterpret_cast<float4*>(myRec + lane * TC_REC);
                 r4[0] = make_float4(__int_as_float(x0), __int_as_float(y0), dx, dy);
                 r4[1] = make_float4(mask, x, y, iZ);
                 r4[2] = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
             }
             __syncwarp();
+            TC_TRACE(3);
 
             // ---------------------------------------------------------------- (iii) gather: 8 units = 4 pixel pairs x NCH... (unit = pair, 64-channel chunk)
-            constexpr int NUNIT = 4 * NCH;
-            float4 tb[3][13];
+            constexpr int NUNIT = (PXW / 2) * NCH;
+            float4 tb[DEPTH][13];
             float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
             const float* img = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl;
 
@@ -461,17 +532,23 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
                     }
                 }
             };
-            issue(0, tb[0]);
-            issue(1, tb[1]);
+            if constexpr (DEPTH == 1) {
 #pragma unroll
-            for (int u = 0; u < NUNIT; ++u) {
-                if (u + 2 < NUNIT) issue(u + 2, tb[(u + 2) % 3]);
-                compute(u, tb[u % 3]);
+                for (int u = 0; u < NUNIT; ++u) { issue(u, tb[0]); compute(u, tb[0]); }
+            } else {
+#pragma unroll
+                for (int u = 0; u < DEPTH - 1; ++u) if (u < NUNIT) issue(u, tb[u]);
+#pragma unroll
+                for (int u = 0; u < NUNIT; ++u) {
+                    if (u + DEPTH - 1 < NUNIT) issue(u + DEPTH - 1, tb[(u + DEPTH - 1) % DEPTH]);
+                    compute(u, tb[u % DEPTH]);
+                }
             }
             __syncwarp();
+            TC_TRACE(4);
 
-            // ---------------------------------------------------------------- (iv) per-pixel 2x7 algebra (lanes 0..7), bundlenet.py:49-74
-            if (lane < 8) {
+            // ---------------------------------------------------------------- (iv) per-pixel 2x7 algebra (lanes 0..PXW-1), bundlenet.py:49-74
+            if (lane < PXW) {
                 float* rec = myRec + lane * TC_REC;
                 const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
                              rc = *reinterpret_cast<const float4*>(rec + 8);
@@ -506,10 +583,12 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             __syncwarp();
 
             // ---------------------------------------------------------------- (v) R rows (A_lo, R_lo) for this warp's 8 pixels
+            TC_TRACE(5);
             if (it > 0) mbar_wait(rfree, (it - 1) & 1);          // the previous tile's MMAs no longer read R / A_lo / R_lo
+            TC_TRACE(6);
 #pragma unroll 2
-            for (int i4 = 0; i4 < 4; ++i4) {
-                const int pl = i4 * 2 + hw, nl = g * 8 + pl;
+            for (int i4 = 0; i4 < PXW / 2; ++i4) {
+                const int pl = i4 * 2 + hw, nl = g * PXW + pl;
                 const float4 e0 = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
                 const float4 e1 = *reinterpret_cast<const float4*>(myRec + pl * TC_REC + 4);
                 const float sn = e1.w;
@@ -544,6 +623,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams 
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(ready);
+            TC_TRACE(7);
         }
         if (cur_b >= 0) flush(span);
     }
@@ -579,24 +659,37 @@ int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan)
     return BANET_OK;
 }
 
-template <int NCH, bool FLY, int MODE>
-static int launch_tc(const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+// tuning knob (not part of the ABI): BANET_TC_GW=8 selects the 8-gather-warp variant (default 16)
+static int tc_gather_warps() {
+    static int gw = 0;
+    if (!gw) { const char* e = getenv("BANET_TC_GW"); gw = (e && atoi(e) == 8) ? 8 : 16; }
+    return gw;
+}
+
+template <int NCH, bool FLY, int MODE, int GW>
+static int launch_tc_gw(const CUtensorMap& tm, const CUtensorMap& tm2, const BuildParams& prm, int grid, cudaStream_t st)
 {
-    auto kern = lm_build_tc_kernel<NCH, FLY, MODE>;
+    auto kern = lm_build_tc_kernel<NCH, FLY, MODE, GW>;
     const int smem = TcSmem<MODE>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("lm_build_tc: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-    kern<<<grid, TC_THREADS, smem, st>>>(tm, prm);
+    kern<<<grid, (TC_GW0 + GW) * 32, smem, st>>>(tm, tm2, prm);
     BANET_CUDA_LAUNCH_CHECK("lm_build_tc_kernel launch");
     return BANET_OK;
 }
 
-template <int NCH, bool FLY>
-static int launch_tc_mode(int mode, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+template <int NCH, bool FLY, int MODE>
+static int launch_tc(const CUtensorMap& tm, const CUtensorMap& tm2, const BuildParams& prm, int grid, cudaStream_t st)
 {
-    if (mode == 1) return launch_tc<NCH, FLY, 1>(tm, prm, grid, st);
-    if (mode == 2) return launch_tc<NCH, FLY, 2>(tm, prm, grid, st);
-    return launch_tc<NCH, FLY, 3>(tm, prm, grid, st);
+    return tc_gather_warps() == 8 ? launch_tc_gw<NCH, FLY, MODE, 8>(tm, tm2, prm, grid, st) : launch_tc_gw<NCH, FLY, MODE, 16>(tm, tm2, prm, grid, st);
+}
+
+template <int NCH, bool FLY>
+static int launch_tc_mode(int mode, const CUtensorMap& tm, const CUtensorMap& tm2, const BuildParams& prm, int grid, cudaStream_t st)
+{
+    if (mode == 1) return launch_tc<NCH, FLY, 1>(tm, tm2, prm, grid, st);
+    if (mode == 2) return launch_tc<NCH, FLY, 2>(tm, tm2, prm, grid, st);
+    return launch_tc<NCH, FLY, 3>(tm, tm2, prm, grid, st);
 }
 
 int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const float* R, const float* T, const float* W,
@@ -609,6 +702,10 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     if (lv->grid_w > 0) rc = make_tmap_f32_3d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->grid_h, lv->grid_w, TC_K, 8, 8, 32);
     else rc = make_tmap_f32_2d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->N, TC_K, TC_TILE, 32);
     if (rc) return rc;
+    const bool fly = lv->conv2_channels == lv->C;
+    CUtensorMap tm2;        // conv2 footprint prefetch boxes: C channels x (12|14)^2 texels
+    rc = make_tmap_f32_nhwc_prefetch(&tm2, lv->conv2, lv->nb, lv->h, lv->w, lv->conv2_channels, lv->C, fly ? 14 : 12, fly ? 14 : 12);
+    if (rc) return rc;
     BuildParams prm;
     prm.nb = lv->nb; prm.N = lv->N; prm.C = lv->C; prm.K = lv->K; prm.h = lv->h; prm.w = lv->w; prm.c2 = lv->conv2_channels;
     prm.conv1 = lv->conv1; prm.conv2 = lv->conv2; prm.intr = lv->intr; prm.p = lv->p; prm.D = lv->D; prm.B = lv->B;
@@ -618,10 +715,10 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
     prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h; prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0;
     prm.hdd_transposed = 1;
-    const bool fly = lv->conv2_channels == lv->C;
+    { const char* e = getenv("BANET_TC_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int nch = lv->C / 64;
-    if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, prm, plan.grid, st);
-    else          rc = fly ? launch_tc_mode<1, true>(mode, tm, prm, plan.grid, st) : launch_tc_mode<1, false>(mode, tm, prm, plan.grid, st);
+    if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);
+    else          rc = fly ? launch_tc_mode<1, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<1, false>(mode, tm, tm2, prm, plan.grid, st);
     if (rc) return rc;
     return launch_lm_reduce(prm, plan.grid, H, g, rbar_sum, nvalid, st);
 }

@@ -51,7 +51,8 @@ def test_tcgen05_precision_modes(mode, use_rna, tol):
 
 def test_tcgen05_accumulator_rounding():
     """Accumulate the same (tf32-exact, positive) tile T times: the exact answer is T * D1.  Documents how the TMEM fp32
-    accumulator rounds (printed); asserts the drift stays below 2^-24 * T (truncation would give ~T * 2^-24 / 2 bias)."""
+    accumulator rounds (printed).  Measured on B200: every accumulation step TRUNCATES (mean -5e-8 relative per step),
+    which is why lm_build_tc keeps TMEM chains short and adds them up round-to-nearest outside the tensor core."""
     g = torch.Generator().manual_seed(3)
     A = _tf32_exact(torch.rand(64, 128, generator=g) + 0.5).cuda(); R = _tf32_exact(torch.rand(64, 160, generator=g) + 0.5).cuda()
     ref1 = A.double().t() @ R.double()
@@ -59,7 +60,8 @@ def test_tcgen05_accumulator_rounding():
         D = _selftest(A, R, 0, 0, repeat=T).double()
         rel = ((D - T * ref1) / (T * ref1))
         print(f"T={T}: mean rel err {rel.mean().item():+.3e}  rms {rel.pow(2).mean().sqrt().item():.3e}  max|.| {rel.abs().max().item():.3e}")
-        assert rel.abs().max().item() < 6e-8 * max(T, 8)
+        assert rel.abs().max().item() < 1.2e-7 * 8 * T          # at most one ulp per accumulation step (8 per tile)
+        assert rel.mean().item() <= 0.0                           # biased toward zero
     Dn = _selftest(-A, R, 0, 0, repeat=256).double()
     reln = (Dn + 256 * ref1) / (256 * ref1)
     print(f"negated A, T=256: mean rel err of |D| {reln.mean().item():+.3e}  (negative => magnitude shrinks => round toward zero)")
