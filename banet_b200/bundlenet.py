@@ -19,7 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
-from ._lib import PREC_FP32_SIMT
+from ._lib import PREC_AUTO
 
 Tensor = torch.Tensor
 
@@ -47,7 +47,7 @@ class BundleNet(torch.nn.Module):
     """Drop-in for reference `BundleNet` (bundlenet.py:86).  `channels` = feature channels C of the pyramid."""
 
     def __init__(self, channels: int, levels: Sequence[str] = ("0", "1", "2", "3"), is_training: bool = True,
-                 reuse_variables=None, vmatrix_batch_scramble: bool = False, precision: int = PREC_FP32_SIMT, seed: int = 7):
+                 reuse_variables=None, vmatrix_batch_scramble: bool = False, precision: int = PREC_AUTO, seed: int = 7):
         super().__init__()
         self.is_training = is_training
         self.reuse_variables = reuse_variables

@@ -165,7 +165,7 @@ class Level:
                           D.data_ptr(), _ptr(B), gw, gh), keep
 
 
-def lm_build(level: Level, R: Tensor, T: Tensor, W: Optional[Tensor], precision: int = _lib.PREC_FP32_SIMT):
+def lm_build(level: Level, R: Tensor, T: Tensor, W: Optional[Tensor], precision: int = _lib.PREC_AUTO):
     """H [nb,P,P], g [nb,P], rbar_sum [nb,C], nvalid [nb] of one iteration at the current (R,T,W)."""
     lib = load()
     st, keep = level.as_struct()
@@ -221,7 +221,7 @@ def lm_solve_update(H: Tensor, g: Tensor, lam: Tensor, R: Tensor, T: Tensor, W: 
 def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
            mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: float = 1000.0,
            lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,
-           vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_FP32_SIMT, workspace: Optional[Tensor] = None):
+           vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_AUTO, workspace: Optional[Tensor] = None):
     """Whole coarse-to-fine solve on the device (banet_lm_run).  Returns new (R,T,W,status); inputs are not modified."""
     lib = load()
     structs, keep = [], []
@@ -254,7 +254,7 @@ def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, 
     return R, T, Wt, status
 
 
-def lm_run_workspace_bytes(levels: Sequence[Level], precision: int = _lib.PREC_FP32_SIMT) -> int:
+def lm_run_workspace_bytes(levels: Sequence[Level], precision: int = _lib.PREC_AUTO) -> int:
     lib = load()
     structs = [lv.as_struct()[0] for lv in levels]
     arr = (BanetLevel * len(structs))(*structs)

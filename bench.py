@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x1", "tf32x2", "tf32x3"],
+                    help="contraction path of the build kernel: auto = tensor cores (tcgen05 tf32 split-A) when K=128, else fp32 SIMT")
     return ap.parse_args()
 
 
@@ -187,18 +189,21 @@ def main():
     C, K, nb, iters = args.channels, args.bases, args.nb, args.iters
     sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 2 + 1000 * rank,
                           device=dev, dtype=torch.float32)
-    levels = [ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B) for l in sc.levels]
+    levels = [ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid) for l in sc.levels]
+    PREC = {"auto": _lib.PREC_AUTO, "fp32": _lib.PREC_FP32_SIMT, "tf32x1": _lib.PREC_TF32X1, "tf32x2": _lib.PREC_TF32X2,
+            "tf32x3": _lib.PREC_TF32X3}[args.precision]
     g = torch.Generator().manual_seed(7)
     dims = [C, 2 * C, 4 * C, 2 * C, C, 1]
     packed = []
     for _ in LEVEL_IDS:       # he-normal lambda-MLP, seed 7 (reference bundlenet.py:105)
         params = [(torch.randn(dims[i], dims[i + 1], generator=g) * (2.0 / dims[i]) ** 0.5, torch.zeros(dims[i + 1])) for i in range(5)]
         packed.append(ops.pack_mlp(params).to(dev))
-    ws = torch.empty(ops.lm_run_workspace_bytes(levels), dtype=torch.uint8, device=dev)
+    ws = torch.empty(ops.lm_run_workspace_bytes(levels, PREC), dtype=torch.uint8, device=dev)
     n_levels, total_iters = len(levels), len(levels) * iters
 
     def step():
-        R, T, W, status = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws)
+        R, T, W, status = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws,
+                                     precision=PREC)
         if world > 1:
             return bdist.all_gather_solution(R, T, W), status
         return (R, T, W), status
@@ -235,16 +240,17 @@ def main():
     per_level = []
     for lv, sl in zip(levels, sc.levels):
         for _ in range(2):
-            ops.lm_build(lv, sc.R0, sc.T0, sc.W0)
+            ops.lm_build(lv, sc.R0, sc.T0, sc.W0, precision=PREC)
         reps = 5
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for _ in range(reps):
-            ops.lm_build(lv, sc.R0, sc.T0, sc.W0)
+            ops.lm_build(lv, sc.R0, sc.T0, sc.W0, precision=PREC)
         e1.record(); torch.cuda.synchronize()
         t = e0.elapsed_time(e1) / reps * 1e-3
         by = nb * algorithmic_bytes_per_pair_iter(sl.N, C, K)
-        per_level.append({"level": f"{sl.w}x{sl.h}", "ms": t * 1e3, "alg_bytes": by, "gbs": by / t / 1e9})
+        by3c = by + nb * 4 * sl.N * 2 * C          # conv2 read as the reference lays it out: [F2|gx|gy] = 3C channels per texel
+        per_level.append({"level": f"{sl.w}x{sl.h}", "ms": t * 1e3, "alg_bytes": by, "gbs": by / t / 1e9, "gbs_3c_layout": by3c / t / 1e9})
     top = per_level[-1]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "lm_build_traffic.json")
@@ -253,15 +259,17 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "lm_build_kernel (+lm_reduce_kernel) @640x480", "achieved": top["gbs"], "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": top["gbs"] / peak, "traffic": traffic, "per_level": per_level,
+    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else "lm_build_tc_kernel"
+    roofline = {"bound": "hbm", "kernel": f"{kname} (+lm_reduce_kernel) @640x480", "achieved": top["gbs"], "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": top["gbs"] / peak, "frac_3c_layout": top["gbs_3c_layout"] / peak,
+                "traffic": traffic, "per_level": per_level,
                 "all_levels_gbs": sum(p["alg_bytes"] for p in per_level) / sum(p["ms"] * 1e-3 for p in per_level) / 1e9}
 
     # ---- e2e: host buffers -> device -> solve -> host, through the public API -------------------------------
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters)
+            e2e = run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, PREC)
         except Exception as ex:      # e.g. not enough pinnable host memory: report, do not fake
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 
@@ -278,7 +286,8 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_pairs": world * nb, "lm_iterations_per_step": total_iters,
-                           "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": "fp32-simt",
+                           "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": args.precision,
+                           "conv2_layout": "[F2|gx|gy] (3C channels, the reference's BundleIteration boundary)",
                            "l2": "inputs (~33 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "parallelism": f"pairs sharded over {world} GPU(s), one all-gather of (R,T,W) per step"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 5),
@@ -288,7 +297,7 @@ def main():
         td.destroy_process_group()
 
 
-def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters):
+def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
     from banet_b200 import ops
     from banet_b200 import dist as bdist
     host = []
@@ -311,9 +320,10 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters):
         for l, tens in zip(sc.levels, host):
             for name, ht in tens.items():
                 getattr(l, name).copy_(ht, non_blocking=True)           # host -> device, every step
-            lvls.append(ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B))
+            lvls.append(ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid))
         R0 = hR.to(dev, non_blocking=True); T0 = hT.to(dev, non_blocking=True); W0 = hW.to(dev, non_blocking=True)
-        R, T, W, status = ops.lm_run(lvls, args.iters, R0, T0, W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws)
+        R, T, W, status = ops.lm_run(lvls, args.iters, R0, T0, W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws,
+                                     precision=prec)
         if world > 1:
             R, T, W = bdist.all_gather_solution(R, T, W)
             return R.cpu(), T.cpu(), W.cpu()
