@@ -378,42 +378,52 @@ __global__ void __launch_bounds__(256)
 lm_reduce_kernel(const BuildParams prm, int grid_build, float* __restrict__ H, float* __restrict__ g,
                  float* __restrict__ rbar_sum, float* __restrict__ nvalid)
 {
-    const int b = blockIdx.x, K = prm.K, C = prm.C, P = 6 + K;
+    const int b = blockIdx.y, K = prm.K, C = prm.C, P = 6 + K;
     const SlotLayout L{K, C};
     const long long p0 = (long long)b * prm.tiles_per_pair, p1 = p0 + prm.tiles_per_pair;
-    // CTAs whose tile range intersects [p0,p1): contiguous range [c0,c1]
-    int c0 = (int)((p0 * grid_build) / prm.total_tiles);
-    while (c0 > 0 && part_begin(prm.total_tiles, grid_build, c0) > p0) --c0;
-    while (c0 + 1 < grid_build && part_begin(prm.total_tiles, grid_build, c0 + 1) <= p0) ++c0;
-    int c1 = c0;
-    while (c1 + 1 < grid_build && part_begin(prm.total_tiles, grid_build, c1 + 1) < p1) ++c1;
-
-    const int nel = L.off_rbar() + C;
-    for (int i = threadIdx.x; i < nel; i += blockDim.x) {
-        int src = i;                                        // element (r, cI) of H_dd lives at cI*K + r in a transposed slot
-        if (prm.hdd_transposed && i < L.off_ext()) { const int r = i / K, cI = i - r * K; src = cI * K + r; }
-        double s = 0.0;
-        for (int c = c0; c <= c1; ++c) {
+    // slots that hold a partial of pair b: one per CTA whose tile range intersects [p0,p1) (a contiguous CTA range)
+    __shared__ const float* s_slot[2 * kMaxSMs + 8];        // a pair can be spread over the whole grid (<= 2 CTAs per SM)
+    __shared__ int s_n;
+    if (threadIdx.x == 0) {
+        int c0 = (int)((p0 * grid_build) / prm.total_tiles);
+        while (c0 + 1 < grid_build && part_begin(prm.total_tiles, grid_build, c0 + 1) <= p0) ++c0;
+        int n = 0;
+        for (int c = c0; c < grid_build && n < 2 * kMaxSMs + 8; ++c) {
             const long long tb = part_begin(prm.total_tiles, grid_build, c), te = part_begin(prm.total_tiles, grid_build, c + 1);
-            if (tb >= te || te <= p0 || tb >= p1) continue;
+            if (tb >= p1) break;
+            if (tb >= te || te <= p0) continue;
             const int span = b - (int)(tb / prm.tiles_per_pair);
-            s += (double)prm.partials[((size_t)c * prm.max_span + span) * prm.slot_floats + src];
+            s_slot[n++] = prm.partials + ((size_t)c * prm.max_span + span) * prm.slot_floats;
         }
+        s_n = n;
+    }
+    __syncthreads();
+    const int nslot = s_n;
+    const int nel = L.off_rbar() + C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nel; i += gridDim.x * blockDim.x) {
+        int src = i;                                        // element (r, cI) of H_dd lives at cI*K + r in a transposed slot
+        int r = 0, cI = 0;
+        if (i < L.off_ext()) {
+            r = i / K; cI = i - r * K;
+            if (cI > r) continue;                           // only the lower triangle is used (and mirrored)
+            if (prm.hdd_transposed) src = cI * K + r;
+        }
+        double s = 0.0;
+        for (int q = 0; q < nslot; ++q) s += (double)s_slot[q][src];
         const float v = (float)s;
         if (i < L.off_ext()) {                              // H_dd: keep the lower triangle, mirror it
-            const int r = i / K, cI = i - r * K;
-            if (cI <= r) { H[((size_t)b * P + 6 + r) * P + 6 + cI] = v; H[((size_t)b * P + 6 + cI) * P + 6 + r] = v; }
+            H[((size_t)b * P + 6 + r) * P + 6 + cI] = v; H[((size_t)b * P + 6 + cI) * P + 6 + r] = v;
         } else if (i < L.off_cc()) {
-            const int r = (i - L.off_ext()) / K, k = (i - L.off_ext()) - r * K;
-            if (r < 6) { H[((size_t)b * P + r) * P + 6 + k] = v; H[((size_t)b * P + 6 + k) * P + r] = v; }
+            const int rr = (i - L.off_ext()) / K, k = (i - L.off_ext()) - rr * K;
+            if (rr < 6) { H[((size_t)b * P + rr) * P + 6 + k] = v; H[((size_t)b * P + 6 + k) * P + rr] = v; }
             else g[(size_t)b * P + 6 + k] = v;
         } else if (i < L.off_rbar()) {
             const int q = i - L.off_cc();
             if (q < 21) {
-                int r = 0, rem = q;
-                while (rem >= 6 - r) { rem -= 6 - r; ++r; }
-                const int cI = r + rem;
-                H[((size_t)b * P + r) * P + cI] = v; H[((size_t)b * P + cI) * P + r] = v;
+                int rr = 0, rem = q;
+                while (rem >= 6 - rr) { rem -= 6 - rr; ++rr; }
+                const int cc = rr + rem;
+                H[((size_t)b * P + rr) * P + cc] = v; H[((size_t)b * P + cc) * P + rr] = v;
             } else if (q < 27) g[(size_t)b * P + q - 21] = v;
             else if (q == 27) nvalid[b] = v;
         } else {
@@ -424,7 +434,9 @@ lm_reduce_kernel(const BuildParams prm, int grid_build, float* __restrict__ H, f
 
 int launch_lm_reduce(const BuildParams& prm, int grid_build, float* H, float* g, float* rbar_sum, float* nvalid, cudaStream_t st)
 {
-    lm_reduce_kernel<<<prm.nb, 256, 0, st>>>(prm, grid_build, H, g, rbar_sum, nvalid);
+    const int nel = prm.K * prm.K + 7 * prm.K + 32 + prm.C;
+    int chunks = (nel + 2047) / 2048; if (chunks < 1) chunks = 1; if (chunks > 16) chunks = 16;
+    lm_reduce_kernel<<<dim3(chunks, prm.nb), 256, 0, st>>>(prm, grid_build, H, g, rbar_sum, nvalid);
     BANET_CUDA_LAUNCH_CHECK("lm_reduce_kernel launch");
     return BANET_OK;
 }
@@ -482,7 +494,7 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
     prm.partials = reinterpret_cast<float*>(ws);
     prm.slot_floats = plan.slot_floats; prm.max_span = plan.max_span;
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
-    prm.grid_w = 0; prm.grid_h = 0; prm.tiles_x = 0; prm.hdd_transposed = 0; prm.trace = nullptr;
+    prm.grid_w = 0; prm.grid_h = 0; prm.tiles_x = 0; prm.hdd_transposed = 0; prm.trace = nullptr; prm.pf_conv2 = 0;
     const bool vec4 = (lv->C % 4 == 0) && (lv->conv2_channels % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(lv->conv1) | reinterpret_cast<uintptr_t>(lv->conv2)) % 16 == 0);
     int rc;

@@ -249,8 +249,10 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                     for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + tn.n0, by);
                 }
             }
-            // conv2 footprint of tile tp, predicted from the flow of tile t (dense grid only)
-            if (grid2d) {
+            // conv2 footprint of tile tp, predicted from the flow of tile t (dense grid only).  Off by default: measured on
+            // B200 it raised DRAM traffic by ~35% (boxes over-cover, lines evicted before use) without shortening the kernel,
+            // whose gather phase is bound by the per-warp dependency chain, not by tap latency (profiles/r01_*).
+            if (grid2d && prm.pf_conv2) {
                 const bool have_bb = mbar_wait_bounded(ready, it & 1, 2000);   // tile t's geometry (and bounding boxes) complete
                 int xmn = INT_MAX, ymn = INT_MAX;
                 if (have_bb && lane < GW) { xmn = sBB[((it & 1) * TC_GWMAX + lane) * 4 + 0]; ymn = sBB[((it & 1) * TC_GWMAX + lane) * 4 + 2]; }
@@ -715,6 +717,7 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
     prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h; prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0;
     prm.hdd_transposed = 1;
+    { const char* e = getenv("BANET_TC_PF_CONV2"); prm.pf_conv2 = (e && atoi(e) == 1) ? 1 : 0; }
     { const char* e = getenv("BANET_TC_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int nch = lv->C / 64;
     if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);

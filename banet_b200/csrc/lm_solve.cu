@@ -15,7 +15,7 @@ __device__ __forceinline__ float selu_f(float x) {
     return scale * (x > 0.f ? x : alpha * expm1f(x));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 lm_lambda_kernel(const float* __restrict__ rbar_sum, int N, int C, const float* __restrict__ mlp, float base,
                  float* __restrict__ lambda_out)
 {
@@ -41,18 +41,22 @@ lm_lambda_kernel(const float* __restrict__ rbar_sum, int N, int C, const float* 
     for (int l = 0; l < 5; ++l) {
         const int cin = dims[l], cout = dims[l + 1];
         const float* Wm = wp; const float* bias = wp + (size_t)cin * cout;
-        for (int j = tid; j < cout; j += blockDim.x) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int i = 0;
-            for (; i + 3 < cin; i += 4) {
-                a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
-                a1 = fmaf(in[i + 1], __ldg(Wm + (size_t)(i + 1) * cout + j), a1);
-                a2 = fmaf(in[i + 2], __ldg(Wm + (size_t)(i + 2) * cout + j), a2);
-                a3 = fmaf(in[i + 3], __ldg(Wm + (size_t)(i + 3) * cout + j), a3);
+        // 8 consecutive lanes share one output neuron j and split the input dimension; lanes of a warp that hold the
+        // same input index read 4 consecutive weights (coalesced 16-B segments), partial sums meet through shuffles
+        for (int j0 = 0; j0 < cout; j0 += blockDim.x / 8) {
+            const int j = j0 + (tid >> 3), part = tid & 7;
+            float a0 = 0.f, a1 = 0.f;
+            if (j < cout) {
+                int i = part;
+                for (; i + 8 < cin; i += 16) {
+                    a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
+                    a1 = fmaf(in[i + 8], __ldg(Wm + (size_t)(i + 8) * cout + j), a1);
+                }
+                for (; i < cin; i += 8) a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
             }
-            for (; i < cin; ++i) a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
-            const float z = ((a0 + a1) + (a2 + a3)) + __ldg(bias + j);
-            out[j] = (l == 4) ? tanhf(z) : selu_f(z);
+            float z = a0 + a1;
+            z += __shfl_xor_sync(0xffffffffu, z, 4); z += __shfl_xor_sync(0xffffffffu, z, 2); z += __shfl_xor_sync(0xffffffffu, z, 1);
+            if (j < cout && part == 0) { z += __ldg(bias + j); out[j] = (l == 4) ? tanhf(z) : selu_f(z); }
         }
         __syncthreads();
         wp = bias + cout;
@@ -72,7 +76,7 @@ int lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp, flo
         cudaError_t e = cudaFuncSetAttribute(lm_lambda_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("lm_lambda smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
     }
-    lm_lambda_kernel<<<nb, 256, smem, st>>>(rbar_sum, N, C, mlp, base, lambda_out);
+    lm_lambda_kernel<<<nb, 1024, smem, st>>>(rbar_sum, N, C, mlp, base, lambda_out);
     BANET_CUDA_LAUNCH_CHECK("lm_lambda_kernel launch");
     return BANET_OK;
 }
@@ -81,7 +85,7 @@ int lm_lambda(const float* rbar_sum, int nb, int N, int C, const float* mlp, flo
 // Damped solve: one CTA per pair, packed lower-triangular Cholesky in shared memory.
 // S = double when the packed matrix fits (P <= 223), float beyond.
 // ------------------------------------------------------------------------------------------------
-constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_THREADS = 1024;
 __host__ __device__ __forceinline__ int tri(int i, int k) { return i * (i + 1) / 2 + k; }
 
 template <typename S>
@@ -103,8 +107,8 @@ lm_solve_kernel(const float* __restrict__ H, const float* __restrict__ g, const 
 
     // load lower triangle (+ damping on the diagonal, bundlenet.py:264-266 / :181-182)
     int bad = 0;
-    for (int i = tid / 16; i < P; i += SOLVE_THREADS / 16) {
-        for (int k = tid % 16; k <= i; k += 16) {
+    for (int i = tid / 32; i < P; i += SOLVE_THREADS / 32) {
+        for (int k = tid % 32; k <= i; k += 32) {
             float v = Hb[(size_t)i * P + k];
             if (!isfinite(v)) bad = 1;
             S sv = (S)v;
@@ -121,7 +125,7 @@ lm_solve_kernel(const float* __restrict__ H, const float* __restrict__ g, const 
     if (bad) atomicOr(&s_flag, 2);
 
     // right-looking Cholesky; column j is scaled one iteration late (saves a barrier per column)
-    const int ta = tid >> 4, tb = tid & 15;
+    const int ta = tid >> 5, tb = tid & 31;
     S inv_prev = (S)1;
     for (int j = 0; j < P; ++j) {
         __syncthreads();
@@ -132,9 +136,9 @@ lm_solve_kernel(const float* __restrict__ H, const float* __restrict__ g, const 
         if (!(d > (S)0)) { if (tid == 0) atomicOr(&s_flag, 1); d = (S)1; }
         const S invd = (S)1 / d;
         inv_prev = (S)1 / sqrt(d);
-        for (int i = j + 1 + ta; i < P; i += 16) {
+        for (int i = j + 1 + ta; i < P; i += 32) {
             const S ci = A[tri(i, j)] * invd;
-            for (int k = j + 1 + tb; k <= i; k += 16) A[tri(i, k)] -= ci * A[tri(k, j)];
+            for (int k = j + 1 + tb; k <= i; k += 32) A[tri(i, k)] -= ci * A[tri(k, j)];
         }
         if (tid == 0) dg[j] = sqrt(d);
     }
