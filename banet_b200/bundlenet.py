@@ -19,6 +19,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import ops
+from . import autograd as _ag
 from ._lib import PREC_AUTO
 
 Tensor = torch.Tensor
@@ -47,13 +48,15 @@ class BundleNet(torch.nn.Module):
     """Drop-in for reference `BundleNet` (bundlenet.py:86).  `channels` = feature channels C of the pyramid."""
 
     def __init__(self, channels: int, levels: Sequence[str] = ("0", "1", "2", "3"), is_training: bool = True,
-                 reuse_variables=None, vmatrix_batch_scramble: bool = False, precision: int = PREC_AUTO, seed: int = 7):
+                 reuse_variables=None, vmatrix_batch_scramble: bool = False, precision: int = PREC_AUTO, seed: int = 7,
+                 exact_sym_grad: bool = False):
         super().__init__()
         self.is_training = is_training
         self.reuse_variables = reuse_variables
         self.channels = channels
         self.vmatrix_batch_scramble = vmatrix_batch_scramble
         self.precision = precision
+        self.exact_sym_grad = exact_sym_grad      # False: the reference's op gradient 2*A*Ghat (utils.cu:648); True: A(Ghat+Ghat^T)
         self.geo = ResizeGeometry()
         g = torch.Generator().manual_seed(seed)
         dims = [channels, 2 * channels, 4 * channels, 2 * channels, channels, 1]
@@ -80,9 +83,18 @@ class BundleNet(torch.nn.Module):
         return ops.compute_coordinates(points2d, _intr_from_tiled(fx, fy, ox, oy), normalize=True)
 
     # ---- one LM iteration ----------------------------------------------------------------------
+    @staticmethod
+    def _wants_grad(*tensors) -> bool:
+        return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+
     def CameraIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, R, T, l2_regularizer_base=None, level=None,
-                        return_aux: bool = False):
-        """reference bundlenet.py:122-191 -> (updatedR, updatedT).  l2_regularizer_base accepted, unused (as there)."""
+                        return_aux: bool = False, differentiable: Optional[bool] = None):
+        """reference bundlenet.py:122-191 -> (updatedR, updatedT).  l2_regularizer_base accepted, unused (as there).
+        differentiable: None = automatically when gradients are being recorded (training path, banet_b200/autograd.py)."""
+        if differentiable or (differentiable is None and self._wants_grad(conv1, conv2, D, R, T, *self.parameters())):
+            Rn, Tn, _ = _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None, R, T, None,
+                                      self.mlp_params(str(level)), None, exact_sym=self.exact_sym_grad)
+            return Rn, Tn
         lv = ops.Level(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None)
         H, g, rbar, nvalid = ops.lm_build(lv, R, T, None, self.precision)
         lam = ops.lm_lambda(rbar, conv1.shape[1], self.mlp_packed(str(level)), 1.0)
@@ -93,8 +105,11 @@ class BundleNet(torch.nn.Module):
         return Rn, Tn
 
     def BundleIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, l2_regularizer_base=None, level=None,
-                        return_aux: bool = False):
+                        return_aux: bool = False, differentiable: Optional[bool] = None):
         """reference bundlenet.py:193-278 -> (updatedR, updatedT, updatedW)."""
+        if differentiable or (differentiable is None and self._wants_grad(conv1, conv2, D, B, R, T, W, *self.parameters())):
+            return _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B, R, T, W,
+                                 self.mlp_params(str(level)), l2_regularizer_base, exact_sym=self.exact_sym_grad)
         lv = ops.Level(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B)
         H, g, rbar, nvalid = ops.lm_build(lv, R, T, W, self.precision)
         base = 1.0 if l2_regularizer_base is None else float(l2_regularizer_base)      # :252-253
