@@ -56,17 +56,16 @@ constexpr int TC_STAGE_R = 5 * TC_TILE * 128;      // 40 KB
 constexpr int TC_REC = 12;                         // floats per pixel record
 
 template <int MODE> struct TcSmem {
-    static constexpr int off_A = 0;                                   // 2 stages (TMA landing zone, also MMA operand A_hi)
-    static constexpr int off_R = 2 * TC_STAGE_A;                      // 1 stage
+    static constexpr int off_A = 0;                                   // 3 stages (TMA landing zone, also MMA operand A_hi)
+    static constexpr int off_R = 3 * TC_STAGE_A;                      // 1 stage
     static constexpr int off_Alo = off_R + TC_STAGE_R;                // 1 stage (MODE >= 2)
     static constexpr int off_Rlo = off_Alo + (MODE >= 2 ? TC_STAGE_A : 0);   // 1 stage (MODE 3)
     static constexpr int off_misc = off_Rlo + (MODE == 3 ? TC_STAGE_R : 0);
-    static constexpr int off_bar = off_misc;                          // 12 mbarriers
-    static constexpr int off_tmem = off_bar + 96;
-    static constexpr int off_pose = off_misc + 128;                   // [2][16] floats
-    static constexpr int off_W = off_pose + 128;                      // [2][128] floats
-    static constexpr int off_rec = off_W + 1024;                      // [64 pixels][TC_REC] floats
-    static constexpr int off_cc = off_rec + TC_TILE * TC_REC * 4;     // [64 pixel slots][28] floats
+    static constexpr int off_bar = off_misc;                          // 14 mbarriers
+    static constexpr int off_tmem = off_bar + 112;
+    static constexpr int off_pose = off_misc + 128;                   // [TC_GWMAX warps][2 pair parities][16] floats
+    static constexpr int off_rec = off_pose + TC_GWMAX * 32 * 4;      // [2 tile parities][64 pixels][TC_REC] floats
+    static constexpr int off_cc = off_rec + 2 * TC_TILE * TC_REC * 4; // [64 pixel slots][28] floats
     static constexpr int off_bb = off_cc + TC_TILE * 28 * 4;          // [2][TC_GWMAX][4] ints: tap-origin bounding boxes
     static constexpr int total = off_bb + 2 * TC_GWMAX * 4 * 4;
     static constexpr int bytes = total + 1024;                        // slack for manual 1024-B alignment
@@ -103,17 +102,16 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::off_bar);
-    uint64_t* fullB = bars;          // [2]  TMA landed
-    uint64_t* emptyB = bars + 2;     // [2]  MMAs that read A stage s have completed
-    uint64_t* ready = bars + 4;      //      R (Alo, Rlo) of the current tile written by all gather warps
-    uint64_t* rfree = bars + 5;      //      MMAs of the current tile completed -> R may be overwritten
-    uint64_t* flushb = bars + 6;     //      every MMA of the span completed
-    uint64_t* tmemfree = bars + 7;   //      lo accumulator drained by the gather warps
-    uint64_t* chain_done = bars + 8; // [2]  every hi-pass MMA of the chain that used accumulator `set` completed
-    uint64_t* drained = bars + 10;   // [2]  hi accumulator `set` drained by the gather warps
+    uint64_t* fullB = bars;          // [3]  TMA landed
+    uint64_t* emptyB = bars + 3;     // [3]  MMAs that read A stage s have completed
+    uint64_t* ready = bars + 6;      //      R (Alo, Rlo) of the current tile written by all gather warps
+    uint64_t* rfree = bars + 7;      //      MMAs of the current tile completed -> R may be overwritten
+    uint64_t* flushb = bars + 8;     //      every MMA of the span completed
+    uint64_t* tmemfree = bars + 9;   //      lo accumulator drained by the gather warps
+    uint64_t* chain_done = bars + 10; // [2] every hi-pass MMA of the chain that used accumulator `set` completed
+    uint64_t* drained = bars + 12;   // [2]  hi accumulator `set` drained by the gather warps
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(base + SM::off_tmem);
     float* sPose = reinterpret_cast<float*>(base + SM::off_pose);
-    float* sW = reinterpret_cast<float*>(base + SM::off_W);
     float* sRec = reinterpret_cast<float*>(base + SM::off_rec);
     float* sCC = reinterpret_cast<float*>(base + SM::off_cc);
     int* sBB = reinterpret_cast<int*>(base + SM::off_bb);
@@ -130,8 +128,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
     const long long t_end   = part_begin(prm.total_tiles, gridDim.x, blockIdx.x + 1);
 
     if (tid == 0) {
-        mbar_init(&fullB[0], 1); mbar_init(&fullB[1], 1);
-        mbar_init(&emptyB[0], 1); mbar_init(&emptyB[1], 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
         mbar_init(ready, GW); mbar_init(rfree, 1);
         mbar_init(flushb, 1); mbar_init(tmemfree, GW);
         mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1);
@@ -159,7 +156,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
         if (lane == 0) {
             int it = 0;
             for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it & 1, ph = (it >> 1) & 1;
+                const int s = it % 3, ph = (it / 3) & 1;
                 const TileCoord tc = tile_coord(prm, t);
                 mbar_wait_sleep(&emptyB[s], ph ^ 1);
                 mbar_arrive_expect_tx(&fullB[s], TC_STAGE_A);
@@ -182,7 +179,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             uint32_t accH = 0, accL = 0;
             const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
             for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it & 1;
+                const int s = it % 3;
                 const int b = (int)(t / prm.tiles_per_pair);
                 if (b != cur_b) {
                     if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++span; }
@@ -266,18 +263,29 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
       }     // warp 3 of warpgroup 0 idle
     } else {
         // ===================================================================== gather warps
+        // Software-pipelined over tiles so that the ALU-only phases hide the tap-load latency of the gather:
+        //   iteration j:  issue loads of unit 0 of tile j
+        //                 2x7 algebra + R rows of tile j-1 (-> MMA j-1)          [hides unit 0's latency]
+        //                 reduce unit 0, issue unit 1
+        //                 b.W + warp geometry of tile j+1 (its basis tile has landed: 3 TMA stages)   [hides unit 1's]
+        //                 remaining units of tile j
         setmaxnreg_inc<GREG>();
         const int g = warp - TC_GW0, hw = lane >> 4, hl = lane & 15;
         const int gtid = tid - TC_GW0 * 32;
         const int blkA = hl >> 3, ccA = hl & 7;                 // this lane's two 16-B chunks of a 128-float row: blocks blkA and 2+blkA
         float wreg[8];
         float rb[NCH * 4];
-        float* myRec = sRec + g * PXW * TC_REC;
+#pragma unroll
+        for (int u = 0; u < NCH * 4; ++u) rb[u] = 0.f;
         float* myCC = sCC + (g * PXW + (lane & (PXW - 1))) * 28;
+        float* myPose = sPose + g * 32;                          // [2 pair parities][16]
         const SlotLayout L{TC_K, C};
         unsigned char* Rs = base + SM::off_R;
-        int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, next_drain = 0;
+        const int ntiles = (int)(t_end - t_begin);
+        int chain = -1, tic = 0, next_drain = 0;                 // TMEM chain bookkeeping (mirrors the MMA issuer), advanced per scaled tile
         bool first_drain = true;
+        int gpar = 1, geom_b = -1;                               // pair parity / pair of the geometry stage
+        int spar = 1, scale_b = -1, sspan = -1;                  // ... of the algebra+scale stage; sspan = slot index within this CTA
 
         // add (or store) this warp's share of a 128 x 160 TMEM region into the slot: H_dd transposed (coalesced), ext rows
         auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
@@ -316,7 +324,6 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&drained[set]);
         };
-
         auto flush = [&](int sp) {
             float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
             for (; next_drain <= chain; ++next_drain) drain_hi(next_drain, slot);
@@ -348,55 +355,34 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             gather_bar<GW * 32>();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmemfree);
+#pragma unroll
+            for (int u = 0; u < NCH * 4; ++u) rb[u] = 0.f;
         };
 
-        for (long long t = t_begin; t < t_end; ++t, ++it) {
-            const int s = it & 1, ph = (it >> 1) & 1;
-            const TileCoord tc = tile_coord(prm, t);
+        // ---- stage G: D~ - D = b.W (geom_a) and the warp geometry of tile j (geom_b2, thread per pixel), records -> sRec[j&1]
+        float mydot = 0.f;
+        auto geom_a = [&](int j) {
+            const TileCoord tc = tile_coord(prm, t_begin + j);
             const int b = tc.b;
-            if (b != cur_b) {
-                if (cur_b >= 0) { flush(span); ++span; }
-                tic = 0; first_drain = true;
-                float* pose = sPose + (span & 1) * 16;
-                float* Wsm = sW + (span & 1) * TC_K;
-                if (g == 0) {
-                    if (lane < 9) pose[lane] = prm.R[b * 9 + lane];
-                    else if (lane < 12) pose[lane] = prm.T[b * 3 + lane - 9];
-                    else if (lane < 16) pose[lane] = prm.intr[b * 4 + lane - 12];
-                    for (int k = lane; k < TC_K; k += 32) Wsm[k] = prm.W[b * TC_K + k];
-                }
-                gather_bar<GW * 32>();
-                {
-                    const float4 w0 = *reinterpret_cast<const float4*>(Wsm + blkA * 32 + ccA * 4);
-                    const float4 w1 = *reinterpret_cast<const float4*>(Wsm + (2 + blkA) * 32 + ccA * 4);
-                    wreg[0] = w0.x; wreg[1] = w0.y; wreg[2] = w0.z; wreg[3] = w0.w;
-                    wreg[4] = w1.x; wreg[5] = w1.y; wreg[6] = w1.z; wreg[7] = w1.w;
-                }
-                if (lane < PXW) {
-#pragma unroll
-                    for (int q = 0; q < 28; ++q) myCC[q] = 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < NCH * 4; ++u) rb[u] = 0.f;
-                cur_b = b;
+            if (b != geom_b) {                                   // new pair: this warp's private copy of pose/intrinsics, W chunks
+                gpar ^= 1; geom_b = b;
+                float* pose = myPose + gpar * 16;
+                __syncwarp();
+                if (lane < 9) pose[lane] = prm.R[b * 9 + lane];
+                else if (lane < 12) pose[lane] = prm.T[b * 3 + lane - 9];
+                else if (lane < 16) pose[lane] = prm.intr[b * 4 + lane - 12];
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * TC_K + blkA * 32 + ccA * 4));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * TC_K + (2 + blkA) * 32 + ccA * 4));
+                wreg[0] = w0.x; wreg[1] = w0.y; wreg[2] = w0.z; wreg[3] = w0.w;
+                wreg[4] = w1.x; wreg[5] = w1.y; wreg[6] = w1.z; wreg[7] = w1.w;
+                __syncwarp();
             }
-            const float* pose = sPose + (span & 1) * 16;
+            const float* pose = myPose + gpar * 16;
+            const int s = j % 3, ph = (j / 3) & 1;
             const unsigned char* As = base + SM::off_A + s * TC_STAGE_A;
-            TC_TRACE(0);
-            if (tic == 0) ++chain;
-            // lazy drain of the previous hi chain, half a chain later (its MMAs completed long ago: no stall)
-            if (tic == TC_CHAIN / 2 && next_drain < chain) {
-                drain_hi(next_drain, prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats);
-                ++next_drain;
-            }
-            if (++tic == TC_CHAIN) tic = 0;
-
-            TC_TRACE(1);
+            float* rec = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
             mbar_wait(&fullB[s], ph);
-            TC_TRACE(2);
-
-            // ---------------------------------------------------------------- (i) D~ - D = b . W for this warp's PXW pixels
-            float mydot = 0.f;
+            mydot = 0.f;
 #pragma unroll
             for (int i4 = 0; i4 < PXW / 2; ++i4) {
                 const int nl = g * PXW + i4 * 2 + hw;
@@ -410,8 +396,13 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                 if (lane == 2 * i4) mydot = dot;
                 if (lane == 2 * i4 + 1) mydot = other;
             }
-            // ---------------------------------------------------------------- (ii) warp geometry, thread per pixel (bundlenet.py:208-224, :231)
-            if (lane < PXW) {
+        };
+        auto geom_b2 = [&](int j) {
+            const TileCoord tc = tile_coord(prm, t_begin + j);
+            const int b = tc.b;
+            const float* pose = myPose + gpar * 16;
+            float* rec = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            if (lane < PXW) {                                    // bundlenet.py:208-224, mask :231
                 int n; bool valid;
                 const int nl = g * PXW + lane;
                 if (grid2d) { const int gx = tc.tx0 + (nl & 7), gy = tc.ty0 + (nl >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
@@ -434,124 +425,35 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                         x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
                     }
                 }
-                if (grid2d) {         // tap-origin bounding box of this warp's pixels, for the L2 prefetcher
-                    int bx = mask != 0.f ? x0 : INT_MAX, by = mask != 0.f ? y0 : INT_MAX;
-#pragma unroll
-                    for (int o = PXW / 2; o > 0; o >>= 1) { bx = min(bx, __shfl_xor_sync((1u << PXW) - 1u, bx, o)); by = min(by, __shfl_xor_sync((1u << PXW) - 1u, by, o)); }
-                    if (lane == 0) { sBB[((it & 1) * TC_GWMAX + g) * 4 + 0] = bx; sBB[((it & 1) * TC_GWMAX + g) * 4 + 2] = by; }
-                }
-                float4* r4 = reinterpret_cast<float4*>(myRec + lane * TC_REC);
+                float4* r4 = reinterpret_cast<float4*>(rec + lane * TC_REC);
                 r4[0] = make_float4(__int_as_float(x0), __int_as_float(y0), dx, dy);
                 r4[1] = make_float4(mask, x, y, iZ);
                 r4[2] = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
             }
             __syncwarp();
-            TC_TRACE(3);
+        };
 
-            // ---------------------------------------------------------------- (iii) gather: 8 units = 4 pixel pairs x NCH... (unit = pair, 64-channel chunk)
-            constexpr int NUNIT = (PXW / 2) * NCH;
-            float4 tb[DEPTH][13];
-            float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
-            const float* img = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl;
-
-            auto issue = [&](int u, float4* t) {
-                const int pl = 2 * (u / NCH) + hw, co = 64 * (u % NCH);
-                const float4 ra = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
-                const float4 rq = *reinterpret_cast<const float4*>(myRec + pl * TC_REC + 4);
-                if (rq.x != 0.f) {
-                    const int x0 = __float_as_int(ra.x), y0 = __float_as_int(ra.y);
-                    const int n = __float_as_int(myRec[pl * TC_REC + 11]);
-                    t[0] = ld_stream_f4(prm.conv1 + ((size_t)b * N + n) * C + 4 * hl + co);
-                    if constexpr (!FLY) {
-                        const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-                        const float* t00 = img + ((size_t)y0 * w + x0) * c2 + co;
-                        const float* t01 = img + ((size_t)y0 * w + x1) * c2 + co;
-                        const float* t10 = img + ((size_t)y1 * w + x0) * c2 + co;
-                        const float* t11 = img + ((size_t)y1 * w + x1) * c2 + co;
-                        t[1] = ldg4(t00); t[2] = ldg4(t01); t[3] = ldg4(t10); t[4] = ldg4(t11);
-                        t[5] = ldg4(t00 + C); t[6] = ldg4(t01 + C); t[7] = ldg4(t10 + C); t[8] = ldg4(t11 + C);
-                        t[9] = ldg4(t00 + 2 * C); t[10] = ldg4(t01 + 2 * C); t[11] = ldg4(t10 + 2 * C); t[12] = ldg4(t11 + 2 * C);
-                    } else {
-                        // F2-only map: 12 texels = rows y0,Y1 x columns XM,x0,X1,XP  +  rows YM,YP x columns x0,X1 (REFLECT-by-one, bundlenet.py:97)
-                        const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
-                        const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
-                        const float* r0 = img + (size_t)y0 * w * c2 + co;
-                        const float* r1 = img + (size_t)Y1 * w * c2 + co;
-                        const float* rm = img + (size_t)YM * w * c2 + co;
-                        const float* rp = img + (size_t)YP * w * c2 + co;
-                        const size_t oM = (size_t)XM * c2, o0 = (size_t)x0 * c2, o1 = (size_t)X1 * c2, oP = (size_t)XP * c2;
-                        t[1] = ldg4(r0 + oM); t[2] = ldg4(r0 + o0); t[3] = ldg4(r0 + o1); t[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
-                        t[5] = ldg4(r1 + oM); t[6] = ldg4(r1 + o0); t[7] = ldg4(r1 + o1); t[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
-                        t[9] = ldg4(rm + o0); t[10] = ldg4(rm + o1); t[11] = ldg4(rp + o0); t[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
-                    }
-                }
-            };
-            auto compute = [&](int u, const float4* t) {
-                const int pl = 2 * (u / NCH) + hw, j = u % NCH;
-                const float4 ra = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
-                const float mask = myRec[pl * TC_REC + 4];
-                if (j == 0) { m11 = m12 = m22 = q1 = q2 = 0.f; }
-                if (mask != 0.f) {
-                    const float dx = ra.z, dy = ra.w;
-                    const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
-                    if constexpr (!FLY) {
-#define BANET_CH(F, CI)                                                                                              \
-                        {                                                                                            \
-                            const float f2 = w00 * t[1].F + w01 * t[2].F + w10 * t[3].F + w11 * t[4].F;              \
-                            const float gx = w00 * t[5].F + w01 * t[6].F + w10 * t[7].F + w11 * t[8].F;              \
-                            const float gy = w00 * t[9].F + w01 * t[10].F + w10 * t[11].F + w11 * t[12].F;           \
-                            const float d = t[0].F - f2;                                                             \
-                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
-                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
-                            rb[4 * j + CI] += fabsf(d);                                                              \
-                        }
-                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
-#undef BANET_CH
-                    } else {
-                        const float h00 = 0.5f * w00, h01 = 0.5f * w01, h10 = 0.5f * w10, h11 = 0.5f * w11;
-                        // t: 1 aM0, 2 a00, 3 a10, 4 aP0, 5 aM1, 6 a01, 7 a11, 8 aP1, 9 a0m, 10 a1m, 11 a0p, 12 a1p  (aXY: column X, row Y)
-#define BANET_CH(F, CI)                                                                                              \
-                        {                                                                                            \
-                            const float f2 = w00 * t[2].F + w01 * t[3].F + w10 * t[6].F + w11 * t[7].F;              \
-                            const float gx = h00 * (t[3].F - t[1].F) + h01 * (t[4].F - t[2].F)                       \
-                                           + h10 * (t[7].F - t[5].F) + h11 * (t[8].F - t[6].F);                      \
-                            const float gy = h00 * (t[6].F - t[9].F) + h10 * (t[11].F - t[2].F)                      \
-                                           + h01 * (t[7].F - t[10].F) + h11 * (t[12].F - t[3].F);                    \
-                            const float d = t[0].F - f2;                                                             \
-                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
-                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
-                            rb[4 * j + CI] += fabsf(d);                                                              \
-                        }
-                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
-#undef BANET_CH
-                    }
-                }
-                if (j == NCH - 1) {
-                    m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
-                    if (hl == 0) {      // overwrite (x0,y0,dx,dy) and n of this pixel's record: no longer needed
-                        *reinterpret_cast<float4*>(myRec + pl * TC_REC) = make_float4(m11, m12, m22, q1);
-                        myRec[pl * TC_REC + 11] = q2;
-                    }
-                }
-            };
-            if constexpr (DEPTH == 1) {
+        // ---- stage S: per-pixel 2x7 algebra (bundlenet.py:49-74), R rows (A_lo, R_lo), TMEM chain bookkeeping of tile j
+        auto s3 = [&](int j) {
+            const TileCoord tc = tile_coord(prm, t_begin + j);
+            if (tc.b != scale_b) {                               // first tile of a pair in this CTA
+                spar ^= 1; scale_b = tc.b; ++sspan; tic = 0; first_drain = true;
+                if (lane < PXW) {
 #pragma unroll
-                for (int u = 0; u < NUNIT; ++u) { issue(u, tb[0]); compute(u, tb[0]); }
-            } else {
-#pragma unroll
-                for (int u = 0; u < DEPTH - 1; ++u) if (u < NUNIT) issue(u, tb[u]);
-#pragma unroll
-                for (int u = 0; u < NUNIT; ++u) {
-                    if (u + DEPTH - 1 < NUNIT) issue(u + DEPTH - 1, tb[(u + DEPTH - 1) % DEPTH]);
-                    compute(u, tb[u % DEPTH]);
+                    for (int q = 0; q < 28; ++q) myCC[q] = 0.f;
                 }
             }
-            __syncwarp();
-            TC_TRACE(4);
-
-            // ---------------------------------------------------------------- (iv) per-pixel 2x7 algebra (lanes 0..PXW-1), bundlenet.py:49-74
+            const float* pose = myPose + spar * 16;
+            float* recw = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            const unsigned char* As = base + SM::off_A + (j % 3) * TC_STAGE_A;
+            if (tic == 0) ++chain;
+            if (tic == TC_CHAIN / 2 && next_drain < chain) {     // lazy drain of the previous hi chain: its MMAs completed long ago
+                drain_hi(next_drain, prm.partials + ((size_t)blockIdx.x * prm.max_span + sspan) * prm.slot_floats);
+                ++next_drain;
+            }
+            if (++tic == TC_CHAIN) tic = 0;
             if (lane < PXW) {
-                float* rec = myRec + lane * TC_REC;
+                float* rec = recw + lane * TC_REC;
                 const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
                              rc = *reinterpret_cast<const float4*>(rec + 8);
                 float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -583,16 +485,17 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                 *reinterpret_cast<float4*>(rec + 4) = make_float4(ext[4], ext[5], ext[6], ext[7]);
             }
             __syncwarp();
-
-            // ---------------------------------------------------------------- (v) R rows (A_lo, R_lo) for this warp's 8 pixels
-            TC_TRACE(5);
-            if (it > 0) mbar_wait(rfree, (it - 1) & 1);          // the previous tile's MMAs no longer read R / A_lo / R_lo
-            TC_TRACE(6);
+        };
+        auto scale = [&](int j) {
+            const TileCoord tc = tile_coord(prm, t_begin + j);
+            float* recw = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            const unsigned char* As = base + SM::off_A + (j % 3) * TC_STAGE_A;
+            if (j > 0) mbar_wait(rfree, (j - 1) & 1);            // the previous tile's MMAs no longer read R / A_lo / R_lo
 #pragma unroll 2
             for (int i4 = 0; i4 < PXW / 2; ++i4) {
                 const int pl = i4 * 2 + hw, nl = g * PXW + pl;
-                const float4 e0 = *reinterpret_cast<const float4*>(myRec + pl * TC_REC);
-                const float4 e1 = *reinterpret_cast<const float4*>(myRec + pl * TC_REC + 4);
+                const float4 e0 = *reinterpret_cast<const float4*>(recw + pl * TC_REC);
+                const float4 e1 = *reinterpret_cast<const float4*>(recw + pl * TC_REC + 4);
                 const float sn = e1.w;
                 const uint32_t offA = blkA * 8192 + sw128_32b_off(nl, ccA);
                 const float4 b0 = *reinterpret_cast<const float4*>(As + offA);
@@ -625,9 +528,116 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(ready);
-            TC_TRACE(7);
+            // last tile of this pair inside this CTA?  then drain / publish its slot now
+            const bool last_of_pair = (j + 1 >= ntiles) || ((int)((t_begin + j + 1) / prm.tiles_per_pair) != tc.b);
+            if (last_of_pair) flush(sspan);
+        };
+
+        // ---- stage L: the tap loads / blends of tile j, (pixel pair, 64-channel chunk) units
+        constexpr int NUNIT = (PXW / 2) * NCH;
+        float4 tb[13];
+        float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
+        auto issue = [&](int j, int b, int u) {
+            const float* rec = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            const int pl = 2 * (u / NCH) + hw, co = 64 * (u % NCH);
+            const float4 ra = *reinterpret_cast<const float4*>(rec + pl * TC_REC);
+            const float mask = rec[pl * TC_REC + 4];
+            if (mask != 0.f) {
+                const int x0 = __float_as_int(ra.x), y0 = __float_as_int(ra.y);
+                const int n = __float_as_int(rec[pl * TC_REC + 11]);
+                const float* img = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl + co;
+                tb[0] = ld_stream_f4(prm.conv1 + ((size_t)b * N + n) * C + 4 * hl + co);
+                if constexpr (!FLY) {
+                    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+                    const float* t00 = img + ((size_t)y0 * w + x0) * c2;
+                    const float* t01 = img + ((size_t)y0 * w + x1) * c2;
+                    const float* t10 = img + ((size_t)y1 * w + x0) * c2;
+                    const float* t11 = img + ((size_t)y1 * w + x1) * c2;
+                    tb[1] = ldg4(t00); tb[2] = ldg4(t01); tb[3] = ldg4(t10); tb[4] = ldg4(t11);
+                    tb[5] = ldg4(t00 + C); tb[6] = ldg4(t01 + C); tb[7] = ldg4(t10 + C); tb[8] = ldg4(t11 + C);
+                    tb[9] = ldg4(t00 + 2 * C); tb[10] = ldg4(t01 + 2 * C); tb[11] = ldg4(t10 + 2 * C); tb[12] = ldg4(t11 + 2 * C);
+                } else {
+                    // F2-only map: 12 texels = rows y0,Y1 x columns XM,x0,X1,XP  +  rows YM,YP x columns x0,X1 (REFLECT-by-one, bundlenet.py:97)
+                    const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
+                    const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
+                    const float* r0 = img + (size_t)y0 * w * c2;
+                    const float* r1 = img + (size_t)Y1 * w * c2;
+                    const float* rm = img + (size_t)YM * w * c2;
+                    const float* rp = img + (size_t)YP * w * c2;
+                    const size_t oM = (size_t)XM * c2, o0 = (size_t)x0 * c2, o1 = (size_t)X1 * c2, oP = (size_t)XP * c2;
+                    tb[1] = ldg4(r0 + oM); tb[2] = ldg4(r0 + o0); tb[3] = ldg4(r0 + o1); tb[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
+                    tb[5] = ldg4(r1 + oM); tb[6] = ldg4(r1 + o0); tb[7] = ldg4(r1 + o1); tb[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
+                    tb[9] = ldg4(rm + o0); tb[10] = ldg4(rm + o1); tb[11] = ldg4(rp + o0); tb[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
+                }
+            }
+        };
+        auto compute = [&](int j, int u) {
+            float* rec = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            const float4* t = tb;
+            const int pl = 2 * (u / NCH) + hw, jc = u % NCH;
+            const float4 ra = *reinterpret_cast<const float4*>(rec + pl * TC_REC);
+            const float mask = rec[pl * TC_REC + 4];
+            if (jc == 0) { m11 = m12 = m22 = q1 = q2 = 0.f; }
+            if (mask != 0.f) {
+                const float dx = ra.z, dy = ra.w;
+                const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+                if constexpr (!FLY) {
+#define BANET_CH(F, CI)                                                                                              \
+                    {                                                                                                \
+                        const float f2 = w00 * t[1].F + w01 * t[2].F + w10 * t[3].F + w11 * t[4].F;                  \
+                        const float gx = w00 * t[5].F + w01 * t[6].F + w10 * t[7].F + w11 * t[8].F;                  \
+                        const float gy = w00 * t[9].F + w01 * t[10].F + w10 * t[11].F + w11 * t[12].F;               \
+                        const float d = t[0].F - f2;                                                                 \
+                        m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);                   \
+                        q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                                  \
+                        rb[4 * jc + CI] += fabsf(d);                                                                 \
+                    }
+                    BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                } else {
+                    const float h00 = 0.5f * w00, h01 = 0.5f * w01, h10 = 0.5f * w10, h11 = 0.5f * w11;
+                    // t: 1 aM0, 2 a00, 3 a10, 4 aP0, 5 aM1, 6 a01, 7 a11, 8 aP1, 9 a0m, 10 a1m, 11 a0p, 12 a1p  (aXY: column X, row Y)
+#define BANET_CH(F, CI)                                                                                              \
+                    {                                                                                                \
+                        const float f2 = w00 * t[2].F + w01 * t[3].F + w10 * t[6].F + w11 * t[7].F;                  \
+                        const float gx = h00 * (t[3].F - t[1].F) + h01 * (t[4].F - t[2].F)                           \
+                                       + h10 * (t[7].F - t[5].F) + h11 * (t[8].F - t[6].F);                          \
+                        const float gy = h00 * (t[6].F - t[9].F) + h10 * (t[11].F - t[2].F)                          \
+                                       + h01 * (t[7].F - t[10].F) + h11 * (t[12].F - t[3].F);                        \
+                        const float d = t[0].F - f2;                                                                 \
+                        m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);                   \
+                        q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                                  \
+                        rb[4 * jc + CI] += fabsf(d);                                                                 \
+                    }
+                    BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                }
+            }
+            if (jc == NCH - 1) {
+                m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
+                if (hl == 0) {      // overwrite (x0,y0,dx,dy) and n of this pixel's record: no longer needed
+                    *reinterpret_cast<float4*>(rec + pl * TC_REC) = make_float4(m11, m12, m22, q1);
+                    rec[pl * TC_REC + 11] = q2;
+                }
+            }
+        };
+
+        if (ntiles > 0) { geom_a(0); geom_b2(0); }
+        for (int j = 0; j < ntiles; ++j) {
+            const int b = (int)((t_begin + j) / prm.tiles_per_pair);
+            // the ALU-only phases of the neighbouring tiles sit behind the first two batches of tap loads of this tile
+            // (measured: spreading them over all four batches is slower — more live state while loads are in flight)
+            issue(j, b, 0);
+            if (j > 0) { s3(j - 1); scale(j - 1); }
+            compute(j, 0);
+            if (NUNIT > 1) issue(j, b, 1);
+            if (j + 1 < ntiles) { geom_a(j + 1); geom_b2(j + 1); }
+            if (NUNIT > 1) compute(j, 1);
+#pragma unroll
+            for (int u = 2; u < NUNIT; ++u) { issue(j, b, u); compute(j, u); }
+            __syncwarp();
         }
-        if (cur_b >= 0) flush(span);
+        if (ntiles > 0) { s3(ntiles - 1); scale(ntiles - 1); }
     }
 
     tc_fence_before_sync();
