@@ -73,6 +73,7 @@ template <int MODE> struct TcSmem {
 
 template <int NT> __device__ __forceinline__ void gather_bar() { asm volatile("bar.sync 1, %0;" :: "n"(NT) : "memory"); }
 __device__ __forceinline__ int reflect_i(int i, int n) { i = i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); return i < 0 ? 0 : i; }
+__device__ __forceinline__ void pf_l2(const float* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define TC_TRACE(slot) do { if (prm.trace && blockIdx.x == 1 && lane == 0 && (g == 0 || g == GW - 1) && it >= 16 && it < 48) \
@@ -85,10 +86,11 @@ __device__ __forceinline__ float hsum16(float v) {            // sum over the 16
 
 struct TileCoord { int b, n0, cnt, tx0, ty0; };
 
-__device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long long t) {
+__device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long long tl) {
     TileCoord tc;
-    tc.b = (int)(t / prm.tiles_per_pair);
-    const int r = (int)(t - (long long)tc.b * prm.tiles_per_pair);
+    const unsigned t = (unsigned)tl, tpp = (unsigned)prm.tiles_per_pair;      // total_tiles < 2^31 (checked on the host): 32-bit maths
+    tc.b = (int)(t / tpp);
+    const int r = (int)(t - (unsigned)tc.b * tpp);
     if (prm.grid_w > 0) { const int tyi = r / prm.tiles_x; tc.ty0 = tyi * 8; tc.tx0 = (r - tyi * prm.tiles_x) * 8; tc.n0 = 0; tc.cnt = TC_TILE; }
     else { tc.n0 = r * TC_TILE; tc.cnt = min(TC_TILE, prm.N - tc.n0); tc.tx0 = tc.ty0 = 0; }
     return tc;
@@ -180,7 +182,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
             for (long long t = t_begin; t < t_end; ++t, ++it) {
                 const int s = it % 3;
-                const int b = (int)(t / prm.tiles_per_pair);
+                const int b = (int)((unsigned)t / (unsigned)prm.tiles_per_pair);
                 if (b != cur_b) {
                     if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++span; }
                     mbar_wait_sleep(tmemfree, (span & 1) ^ 1);    // lo accumulator drained by the previous span's flush
@@ -529,7 +531,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(ready);
             // last tile of this pair inside this CTA?  then drain / publish its slot now
-            const bool last_of_pair = (j + 1 >= ntiles) || ((int)((t_begin + j + 1) / prm.tiles_per_pair) != tc.b);
+            const bool last_of_pair = (j + 1 >= ntiles) || ((int)((unsigned)(t_begin + j + 1) / (unsigned)prm.tiles_per_pair) != tc.b);
             if (last_of_pair) flush(sspan);
         };
 
@@ -568,6 +570,40 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                     tb[1] = ldg4(r0 + oM); tb[2] = ldg4(r0 + o0); tb[3] = ldg4(r0 + o1); tb[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
                     tb[5] = ldg4(r1 + oM); tb[6] = ldg4(r1 + o0); tb[7] = ldg4(r1 + o1); tb[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
                     tb[9] = ldg4(rm + o0); tb[10] = ldg4(rm + o1); tb[11] = ldg4(rp + o0); tb[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
+                }
+            }
+        };
+        auto pf_unit = [&](int j, int b, int u) {        // L2 prefetch of exactly the lines issue(j,b,u) will load
+            const float* rec = sRec + ((j & 1) * TC_TILE + g * PXW) * TC_REC;
+            const int pl = 2 * (u / NCH) + hw, co = 64 * (u % NCH);
+            const float4 ra = *reinterpret_cast<const float4*>(rec + pl * TC_REC);
+            const float mask = rec[pl * TC_REC + 4];
+            if (mask != 0.f) {
+                const int x0 = __float_as_int(ra.x), y0 = __float_as_int(ra.y);
+                const int n = __float_as_int(rec[pl * TC_REC + 11]);
+                const float* img = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl + co;
+                
+                if constexpr (!FLY) {
+                    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+                    const float* t00 = img + ((size_t)y0 * w + x0) * c2;
+                    const float* t01 = img + ((size_t)y0 * w + x1) * c2;
+                    const float* t10 = img + ((size_t)y1 * w + x0) * c2;
+                    const float* t11 = img + ((size_t)y1 * w + x1) * c2;
+                    pf_l2(t00); pf_l2(t01); pf_l2(t10); pf_l2(t11);
+                    pf_l2(t00 + C); pf_l2(t01 + C); pf_l2(t10 + C); pf_l2(t11 + C);
+                    pf_l2(t00 + 2 * C); pf_l2(t01 + 2 * C); pf_l2(t10 + 2 * C); pf_l2(t11 + 2 * C);
+                } else {
+                    // F2-only map: 12 texels = rows y0,Y1 x columns XM,x0,X1,XP  +  rows YM,YP x columns x0,X1 (REFLECT-by-one, bundlenet.py:97)
+                    const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
+                    const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
+                    const float* r0 = img + (size_t)y0 * w * c2;
+                    const float* r1 = img + (size_t)Y1 * w * c2;
+                    const float* rm = img + (size_t)YM * w * c2;
+                    const float* rp = img + (size_t)YP * w * c2;
+                    const size_t oM = (size_t)XM * c2, o0 = (size_t)x0 * c2, o1 = (size_t)X1 * c2, oP = (size_t)XP * c2;
+                    pf_l2(r0 + oM); pf_l2(r0 + o0); pf_l2(r0 + o1); pf_l2(r0 + oP);      // aM0 a00 a10 aP0
+                    pf_l2(r1 + oM); pf_l2(r1 + o0); pf_l2(r1 + o1); pf_l2(r1 + oP);      // aM1 a01 a11 aP1
+                    pf_l2(rm + o0); pf_l2(rm + o1); pf_l2(rp + o0); pf_l2(rp + o1);   // a0m a1m a0p a1p
                 }
             }
         };
@@ -614,8 +650,10 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
                 }
             }
             if (jc == NCH - 1) {
+                // totals overwrite (x0,y0,dx,dy) / n of this pixel's record, which are no longer needed
+                // (five independent butterflies pipeline better than a packed 8-shuffle reduction: measured 2.48 vs 2.63 ms)
                 m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
-                if (hl == 0) {      // overwrite (x0,y0,dx,dy) and n of this pixel's record: no longer needed
+                if (hl == 0) {
                     *reinterpret_cast<float4*>(rec + pl * TC_REC) = make_float4(m11, m12, m22, q1);
                     rec[pl * TC_REC + 11] = q2;
                 }
@@ -624,14 +662,21 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
 
         if (ntiles > 0) { geom_a(0); geom_b2(0); }
         for (int j = 0; j < ntiles; ++j) {
-            const int b = (int)((t_begin + j) / prm.tiles_per_pair);
+            const int b = (int)((unsigned)(t_begin + j) / (unsigned)prm.tiles_per_pair);
             // the ALU-only phases of the neighbouring tiles sit behind the first two batches of tap loads of this tile
             // (measured: spreading them over all four batches is slower — more live state while loads are in flight)
             issue(j, b, 0);
             if (j > 0) { s3(j - 1); scale(j - 1); }
             compute(j, 0);
             if (NUNIT > 1) issue(j, b, 1);
-            if (j + 1 < ntiles) { geom_a(j + 1); geom_b2(j + 1); }
+            if (j + 1 < ntiles) {
+                geom_a(j + 1); geom_b2(j + 1);
+                if (prm.pf_taps) {       // one tile of lead: by the time tile j+1's taps are loaded they sit in L2
+                    const int bn = (int)((unsigned)(t_begin + j + 1) / (unsigned)prm.tiles_per_pair);
+#pragma unroll
+                    for (int u = 0; u < NUNIT; ++u) pf_unit(j + 1, bn, u);
+                }
+            }
             if (NUNIT > 1) compute(j, 1);
 #pragma unroll
             for (int u = 2; u < NUNIT; ++u) { issue(j, b, u); compute(j, u); }
@@ -650,7 +695,7 @@ bool tc_supported(const banet_level_t* lv)
 {
     return lv->K == TC_K && (lv->C == 64 || lv->C == 128) && (lv->conv2_channels == lv->C || lv->conv2_channels == 3 * lv->C) &&
            ((reinterpret_cast<uintptr_t>(lv->conv1) | reinterpret_cast<uintptr_t>(lv->conv2) | reinterpret_cast<uintptr_t>(lv->B)) % 16 == 0) &&
-           (long long)lv->nb * lv->N < (1LL << 31);
+           (long long)lv->nb * lv->N < (1LL << 31) && (long long)lv->nb * ((lv->N + 63) / 64 + 80) < (1LL << 31);
 }
 
 int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan)
@@ -728,6 +773,7 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h; prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0;
     prm.hdd_transposed = 1;
     { const char* e = getenv("BANET_TC_PF_CONV2"); prm.pf_conv2 = (e && atoi(e) == 1) ? 1 : 0; }
+    { const char* e = getenv("BANET_TC_PF_TAPS"); prm.pf_taps = (e && atoi(e) == 1) ? 1 : 0; }
     { const char* e = getenv("BANET_TC_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int nch = lv->C / 64;
     if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);
