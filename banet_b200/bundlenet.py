@@ -91,7 +91,7 @@ class BundleNet(torch.nn.Module):
                         return_aux: bool = False, differentiable: Optional[bool] = None):
         """reference bundlenet.py:122-191 -> (updatedR, updatedT).  l2_regularizer_base accepted, unused (as there).
         differentiable: None = automatically when gradients are being recorded (training path, banet_b200/autograd.py)."""
-        if differentiable or (differentiable is None and self._wants_grad(conv1, conv2, D, R, T, *self.parameters())):
+        if differentiable or (differentiable is None and not return_aux and self._wants_grad(conv1, conv2, D, R, T, *self.parameters())):
             Rn, Tn, _ = _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None, R, T, None,
                                       self.mlp_params(str(level)), None, exact_sym=self.exact_sym_grad)
             return Rn, Tn
@@ -107,7 +107,7 @@ class BundleNet(torch.nn.Module):
     def BundleIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, l2_regularizer_base=None, level=None,
                         return_aux: bool = False, differentiable: Optional[bool] = None):
         """reference bundlenet.py:193-278 -> (updatedR, updatedT, updatedW)."""
-        if differentiable or (differentiable is None and self._wants_grad(conv1, conv2, D, B, R, T, W, *self.parameters())):
+        if differentiable or (differentiable is None and not return_aux and self._wants_grad(conv1, conv2, D, B, R, T, W, *self.parameters())):
             return _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B, R, T, W,
                                  self.mlp_params(str(level)), l2_regularizer_base, exact_sym=self.exact_sym_grad)
         lv = ops.Level(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B)
