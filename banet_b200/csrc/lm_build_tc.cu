@@ -102,7 +102,7 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
 {
     using SM = TcSmem<MODE>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays in the shared state space (LDS/STS)
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::off_bar);
     uint64_t* fullB = bars;          // [3]  TMA landed
     uint64_t* emptyB = bars + 3;     // [3]  MMAs that read A stage s have completed
@@ -716,6 +716,13 @@ int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan)
     return BANET_OK;
 }
 
+int lm_build_tc6_launch(int mode, bool fly, int nch, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st);
+// tuning knob (not part of the ABI): BANET_TC_GEN=5 selects the previous kernel generation (default 6: helper warpgroup)
+static int tc_generation() {
+    static int gen = 0;
+    if (!gen) { const char* e = getenv("BANET_TC_GEN"); gen = (e && atoi(e) == 5) ? 5 : 6; }
+    return gen;
+}
 // tuning knob (not part of the ABI): BANET_TC_GW=8 selects the 8-gather-warp variant (default 16)
 static int tc_gather_warps() {
     static int gw = 0;
@@ -776,7 +783,8 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     { const char* e = getenv("BANET_TC_PF_TAPS"); prm.pf_taps = (e && atoi(e) == 1) ? 1 : 0; }
     { const char* e = getenv("BANET_TC_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int nch = lv->C / 64;
-    if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);
+    if (tc_generation() == 6) rc = lm_build_tc6_launch(mode, fly, nch, tm, prm, plan.grid, st);
+    else if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);
     else          rc = fly ? launch_tc_mode<1, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<1, false>(mode, tm, tm2, prm, plan.grid, st);
     if (rc) return rc;
     return launch_lm_reduce(prm, plan.grid, H, g, rbar_sum, nvalid, st);

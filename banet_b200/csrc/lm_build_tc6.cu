@@ -1,0 +1,627 @@
+// lm_build_tc6.cu — tensor-core build kernel, generation 6: the per-pixel scalar phases move to a helper warpgroup.
+//
+// Same contract, slot layout and precision modes as lm_build_tc.cu (read its header first).  What changes is WHO does what:
+//
+//   warpgroup 0   warp 0 TMA producer | warp 1 tcgen05.mma issuer | warp 2 L2 prefetcher | warp 3 idle      (24 regs)
+//   warpgroups 1-4  16 gather warps, 4 pixels each per tile: ONLY  records -> 13 tap loads -> blend/accumulate -> M,q   (96 regs)
+//   warpgroup 5   4 helper warps, 16 pixels each per tile, full lane efficiency:                               (72 regs)
+//                   geometry of tile j+1 : b.W (warp per pixel), warp / mask / tap offsets (thread per pixel) -> records
+//                   algebra of tile j    : 2x7 per-pixel algebra (thread per pixel, H_cc/g_c partials in registers),
+//                                          R rows (A_lo, R_lo) (warp per row, lanes over the 128 basis columns) -> MMA
+//                   TMEM drains (one lane quadrant per helper warp), slot publication
+//   mbarriers: recs[3] helpers->gather (records of tile j ready), gath[3] gather->helpers (M,q of tile j written);
+//   everything else (fullB/emptyB/ready/rfree/chain_done/drained/flushb/tmemfree) as in generation 5.
+#include "common.cuh"
+#include "lm_build.h"
+#include "tc_utils.cuh"
+#include "tmap.h"
+#include <stdlib.h>
+
+namespace banet { namespace v6 {
+using namespace tc;
+
+constexpr int TILE = 64, GW = 16, HW = 4, W0 = 4;
+constexpr int THREADS = (W0 + GW + HW) * 32;          // 768
+constexpr int KB = 128, NN = 160;
+constexpr int STAGE_A = 4 * TILE * 128, STAGE_R = 5 * TILE * 128;
+constexpr int REC = 16, NREC = 2;     // record buffers: geometry of tile j+1 overlaps gather / algebra of tile j
+constexpr int CHAIN = 8, TMEM_COLS = 512, ACCL = 320;
+
+template <int MODE> struct Smem {
+    static constexpr int off_A = 0;                                    // 3 stages
+    static constexpr int off_R = 3 * STAGE_A;
+    static constexpr int off_Alo = off_R + STAGE_R;
+    static constexpr int off_Rlo = off_Alo + (MODE >= 2 ? STAGE_A : 0);
+    static constexpr int off_misc = off_Rlo + (MODE == 3 ? STAGE_R : 0);
+    static constexpr int off_bar = off_misc;                           // 22 mbarriers
+    static constexpr int off_tmem = off_bar + 22 * 8;
+    static constexpr int off_tile = off_misc + 192;                    // [NREC][4] ints: pair index of the tile in record buffer s
+    static constexpr int off_pose = off_tile + 64;                     // [HW][2 parities][16] floats
+    static constexpr int off_w = off_pose + HW * 2 * 16 * 4;          // [2 parities][128] floats: W of the pair (identical writes by every helper warp)
+    static constexpr int off_rec = off_w + 2 * 128 * 4;         // [NREC][TILE][REC] floats
+    static constexpr int off_rbs = off_rec + NREC * TILE * REC * 4;       // [GW][128] floats: rbar hand-over gather -> helpers
+    static constexpr int total = off_rbs + GW * 128 * 4;
+    static constexpr int bytes = total + 512;
+};
+
+__device__ __forceinline__ long long gtime6() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// debug timeline (BANET_TC_TRACE_PTR): CTA 1, gather warp 0 (role 0) and helper warp 0 (role 1), tiles 16..47, 12 stamps each
+#ifdef BANET_TC6_TRACE_ON
+#define TC6_TRACE(role, it, slot) do { if (prm.trace && blockIdx.x == 1 && lane == 0 && (it) >= 16 && (it) < 48) \
+        prm.trace[(((role) * 32 + ((it) - 16)) * 12) + (slot)] = gtime6(); } while (0)
+#else
+#define TC6_TRACE(role, it, slot) do { } while (0)
+#endif
+template <int NT> __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, %0;" :: "n"(NT) : "memory"); }
+__device__ __forceinline__ int reflect_i(int i, int n) { i = i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); return i < 0 ? 0 : i; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float hsum16(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+struct TileCoord { int b, n0, cnt, tx0, ty0; };
+__device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long long tl) {
+    TileCoord tc;
+    const unsigned t = (unsigned)tl, tpp = (unsigned)prm.tiles_per_pair;
+    tc.b = (int)(t / tpp);
+    const int r = (int)(t - (unsigned)tc.b * tpp);
+    if (prm.grid_w > 0) { const int tyi = r / prm.tiles_x; tc.ty0 = tyi * 8; tc.tx0 = (r - tyi * prm.tiles_x) * 8; tc.n0 = 0; tc.cnt = TILE; }
+    else { tc.n0 = r * TILE; tc.cnt = min(TILE, prm.N - tc.n0); tc.tx0 = tc.ty0 = 0; }
+    return tc;
+}
+
+template <int NCH, bool FLY, int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams prm)
+{
+    using SM = Smem<MODE>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // align through the 32-bit shared address so that the compiler keeps every access in the shared state space (LDS/STS, not generic LD/ST)
+    unsigned char* base = smem_raw + ((512u - (smem_u32(smem_raw) & 511u)) & 511u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::off_bar);
+    uint64_t* fullB = bars;            // [3] TMA landed
+    uint64_t* emptyB = bars + 3;       // [3] MMAs reading A stage s completed
+    uint64_t* ready = bars + 6;        //     R (Alo,Rlo) of the tile written by the 4 helper warps
+    uint64_t* rfree = bars + 7;        //     MMAs of the tile completed
+    uint64_t* flushb = bars + 8;       //     every MMA of the span completed
+    uint64_t* tmemfree = bars + 9;     //     lo accumulator drained
+    uint64_t* chain_done = bars + 10;  // [2]
+    uint64_t* drained = bars + 12;     // [2]
+    uint64_t* recs = bars + 14;        // [NREC] records of the tile in buffer s written (count HW)
+    uint64_t* gath = bars + 17;        // [NREC] M,q of the tile in buffer s written (count GW)
+    uint64_t* rbdump = bars + 20;      //     gather warps parked their rbar partials (count GW)
+    uint64_t* rbfree = bars + 21;      //     helpers consumed them (count HW)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(base + SM::off_tmem);
+    int* sTile = reinterpret_cast<int*>(base + SM::off_tile);
+    float* sPose = reinterpret_cast<float*>(base + SM::off_pose);
+    float* sW = reinterpret_cast<float*>(base + SM::off_w);
+    float* sRec = reinterpret_cast<float*>(base + SM::off_rec);
+    float* sRbs = reinterpret_cast<float*>(base + SM::off_rbs);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int N = prm.N, h = prm.h, w = prm.w, c2 = prm.c2;
+    const bool grid2d = prm.grid_w > 0;
+    constexpr int C = 64 * NCH;
+    const long long t_begin = part_begin(prm.total_tiles, gridDim.x, blockIdx.x);
+    const long long t_end   = part_begin(prm.total_tiles, gridDim.x, blockIdx.x + 1);
+    const int ntiles = (int)(t_end - t_begin);
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); mbar_init(&recs[i], HW); mbar_init(&gath[i], GW); }
+        mbar_init(ready, HW); mbar_init(rfree, 1); mbar_init(flushb, 1); mbar_init(tmemfree, HW);
+        mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1); mbar_init(&drained[0], HW); mbar_init(&drained[1], HW);
+        mbar_init(rbdump, GW); mbar_init(rbfree, HW);
+        fence_barrier_init();
+        prefetch_tmap(&tmapB);
+    }
+    if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
+    for (int i = tid; i < TILE * 8; i += THREADS) {       // pad chunks of R / R_lo's 5th block stay zero
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<float4*>(base + SM::off_R + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 3) *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+
+    if (warp < W0) {
+      setmaxnreg_dec<24>();
+      if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (long long t = t_begin; t < t_end; ++t, ++it) {
+                const int s = it % 3, ph = (it / 3) & 1;
+                const TileCoord tc = tile_coord(prm, t);
+                mbar_wait_sleep(&emptyB[s], ph ^ 1);
+                mbar_arrive_expect_tx(&fullB[s], STAGE_A);
+                unsigned char* dst = base + SM::off_A + s * STAGE_A;
+                if (grid2d) {
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[s]);
+                } else {
+                    const int row = tc.b * N + tc.n0;
+#pragma unroll
+                    for (int blk = 0; blk < 4; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[s]);
+                }
+            }
+        }
+      } else if (warp == 1) {
+        // ===================================================================== MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, NN);
+            int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, set = 0;
+            uint32_t accH = 0, accL = 0;
+            const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
+            for (long long t = t_begin; t < t_end; ++t, ++it) {
+                const int s = it % 3;
+                const int b = (int)((unsigned)t / (unsigned)prm.tiles_per_pair);
+                if (b != cur_b) {
+                    if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++span; }
+                    mbar_wait_sleep(tmemfree, (span & 1) ^ 1);
+                    accL = 0; cur_b = b; tic = 0;
+                }
+                if (tic == 0) { ++chain; set = chain & 1; mbar_wait_sleep(&drained[set], ((chain >> 1) & 1) ^ 1); accH = 0; }
+                mbar_wait_sleep(ready, it & 1);
+                tc_fence_after_sync();
+                const uint32_t ahi = smem_u32(base + SM::off_A + s * STAGE_A);
+#pragma unroll
+                for (int pass = 0; pass < MODE; ++pass) {
+                    const uint32_t a0 = (pass == 1) ? alo : ahi;
+                    const uint32_t r0 = (pass == 2) ? rlo : rhi;
+                    const uint32_t dcol = tmem + (pass == 0 ? set * NN : ACCL);
+#pragma unroll
+                    for (int kk = 0; kk < TILE / 8; ++kk) {
+                        mma_tf32_ss(dcol, make_desc_mn_sw128_32b(a0 + kk * 1024, 8192, 512),
+                                    make_desc_mn_sw128_32b(r0 + kk * 1024, 8192, 512), idesc, pass == 0 ? accH : accL);
+                        if (pass == 0) accH = 1; else accL = 1;
+                    }
+                }
+                mma_commit(&emptyB[s]);
+                mma_commit(rfree);
+                if (++tic == CHAIN) { mma_commit(&chain_done[set]); tic = 0; }
+            }
+            if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); }
+        }
+      } else if (warp == 2) {
+        // ===================================================================== L2 prefetcher of the streaming inputs (conv1, p, D)
+        int it = 0;
+        for (long long t = t_begin; t < t_end; ++t, ++it) {
+            const long long tp = t + 2;
+            if (tp >= t_end) break;
+            mbar_wait_bounded(&fullB[it % 3], (it / 3) & 1, 4000);      // pacing only (best effort)
+            const TileCoord tn = tile_coord(prm, tp);
+            if (grid2d) {
+                if (lane < 8) {
+                    const int gy = tn.ty0 + lane;
+                    if (gy < prm.grid_h && tn.tx0 < prm.grid_w) {
+                        const size_t n = (size_t)gy * prm.grid_w + tn.tx0;
+                        const int wpx = min(8, prm.grid_w - tn.tx0);
+                        prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + n) * C, (uint32_t)(wpx * C * 4));
+                        if ((n & 3) == 0 && (N & 3) == 0) {
+                            const uint32_t by = (uint32_t)(((wpx * 4) + 15) & ~15);
+                            prefetch_l2_bulk(prm.D + (size_t)tn.b * N + n, by);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + n, by);
+                        }
+                    }
+                }
+            } else if (lane == 0) {
+                prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + tn.n0) * C, (uint32_t)(tn.cnt * C * 4));
+                if ((N & 3) == 0) {
+                    const uint32_t by = (uint32_t)(((tn.cnt * 4) + 15) & ~15);
+                    prefetch_l2_bulk(prm.D + (size_t)tn.b * N + tn.n0, by);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + tn.n0, by);
+                }
+            }
+        }
+      }
+    } else if (warp < W0 + GW) {
+        // ===================================================================== gather warps: records -> taps -> M, q
+        setmaxnreg_inc<96>();
+        const int g = warp - W0, hw = lane >> 4, hl = lane & 15;
+        constexpr int PXW = TILE / GW;                       // 4 pixels per warp and tile
+        constexpr int NUNIT = (PXW / 2) * NCH;
+        float rb[NCH * 4];
+#pragma unroll
+        for (int u = 0; u < NCH * 4; ++u) rb[u] = 0.f;
+        float4 tb[13];
+        float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
+        int cur_b = -1, ndump = 0;
+
+        auto dump_rb = [&]() {
+            if (ndump > 0) mbar_wait(rbfree, (ndump - 1) & 1);       // helpers consumed the previous hand-over
+#pragma unroll
+            for (int u = 0; u < NCH * 4; ++u) rb[u] += __shfl_xor_sync(0xffffffffu, rb[u], 16);
+            if (hw == 0) {
+#pragma unroll
+                for (int j = 0; j < NCH; ++j)
+                    *reinterpret_cast<float4*>(sRbs + g * 128 + 64 * j + 4 * hl) = make_float4(rb[4 * j], rb[4 * j + 1], rb[4 * j + 2], rb[4 * j + 3]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rbdump);
+#pragma unroll
+            for (int u = 0; u < NCH * 4; ++u) rb[u] = 0.f;
+            ++ndump;
+        };
+
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % NREC;
+            if (g == 0) TC6_TRACE(0, j, 0);
+            mbar_wait(&recs[s], (j / NREC) & 1);
+            if (g == 0) TC6_TRACE(0, j, 1);
+            const int b = sTile[s * 4];
+            if (b != cur_b) { if (cur_b >= 0) dump_rb(); cur_b = b; }
+            float* rec = sRec + (s * TILE + g * PXW) * REC;
+            const float* c1b = prm.conv1 + (size_t)b * N * C + 4 * hl;
+            const float* imgb = prm.conv2 + (size_t)b * h * w * c2 + 4 * hl;
+#pragma unroll
+            for (int u = 0; u < NUNIT; ++u) {
+                const int pl = 2 * (u / NCH) + hw, co = 64 * (u % NCH), jc = u % NCH;
+                const float mask = rec[pl * REC + 4];
+                if (mask != 0.f) {
+                    const uint4 o = *reinterpret_cast<const uint4*>(rec + pl * REC);
+                    const int n = __float_as_int(rec[pl * REC + 11]);
+                    const float* img = imgb + co;
+                    tb[0] = ld_stream_f4(c1b + (size_t)n * C + co);
+                    if constexpr (!FLY) {
+                        const float* t00 = img + o.x; const float* t01 = img + o.y; const float* t10 = img + o.z; const float* t11 = img + o.w;
+                        tb[1] = ldg4(t00); tb[2] = ldg4(t01); tb[3] = ldg4(t10); tb[4] = ldg4(t11);
+                        tb[5] = ldg4(t00 + C); tb[6] = ldg4(t01 + C); tb[7] = ldg4(t10 + C); tb[8] = ldg4(t11 + C);
+                        tb[9] = ldg4(t00 + 2 * C); tb[10] = ldg4(t01 + 2 * C); tb[11] = ldg4(t10 + 2 * C); tb[12] = ldg4(t11 + 2 * C);
+                    } else {
+                        const int x0 = (int)o.x, y0 = (int)o.y;
+                        const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
+                        const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
+                        const float* r0 = img + (uint32_t)(y0 * w * c2); const float* r1 = img + (uint32_t)(Y1 * w * c2);
+                        const float* rm = img + (uint32_t)(YM * w * c2); const float* rp = img + (uint32_t)(YP * w * c2);
+                        const uint32_t oM = XM * c2, o0 = x0 * c2, o1 = X1 * c2, oP = XP * c2;
+                        tb[1] = ldg4(r0 + oM); tb[2] = ldg4(r0 + o0); tb[3] = ldg4(r0 + o1); tb[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
+                        tb[5] = ldg4(r1 + oM); tb[6] = ldg4(r1 + o0); tb[7] = ldg4(r1 + o1); tb[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
+                        tb[9] = ldg4(rm + o0); tb[10] = ldg4(rm + o1); tb[11] = ldg4(rp + o0); tb[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
+                    }
+                }
+                if (jc == 0) { m11 = m12 = m22 = q1 = q2 = 0.f; }
+                if (mask != 0.f) {
+                    const float2 dxy = *reinterpret_cast<const float2*>(rec + pl * REC + 12);
+                    const float dx = dxy.x, dy = dxy.y;
+                    const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+                    const float4* t = tb;
+                    if constexpr (!FLY) {
+#define BANET_CH(F, CI)                                                                                              \
+                        {                                                                                            \
+                            const float f2 = w00 * t[1].F + w01 * t[2].F + w10 * t[3].F + w11 * t[4].F;              \
+                            const float gx = w00 * t[5].F + w01 * t[6].F + w10 * t[7].F + w11 * t[8].F;              \
+                            const float gy = w00 * t[9].F + w01 * t[10].F + w10 * t[11].F + w11 * t[12].F;           \
+                            const float d = t[0].F - f2;                                                             \
+                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
+                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
+                            rb[4 * jc + CI] += fabsf(d);                                                             \
+                        }
+                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                    } else {
+                        const float h00 = 0.5f * w00, h01 = 0.5f * w01, h10 = 0.5f * w10, h11 = 0.5f * w11;
+#define BANET_CH(F, CI)                                                                                              \
+                        {                                                                                            \
+                            const float f2 = w00 * t[2].F + w01 * t[3].F + w10 * t[6].F + w11 * t[7].F;              \
+                            const float gx = h00 * (t[3].F - t[1].F) + h01 * (t[4].F - t[2].F)                       \
+                                           + h10 * (t[7].F - t[5].F) + h11 * (t[8].F - t[6].F);                      \
+                            const float gy = h00 * (t[6].F - t[9].F) + h10 * (t[11].F - t[2].F)                      \
+                                           + h01 * (t[7].F - t[10].F) + h11 * (t[12].F - t[3].F);                    \
+                            const float d = t[0].F - f2;                                                             \
+                            m11 = fmaf(gx, gx, m11); m12 = fmaf(gx, gy, m12); m22 = fmaf(gy, gy, m22);               \
+                            q1 = fmaf(gx, d, q1); q2 = fmaf(gy, d, q2);                                              \
+                            rb[4 * jc + CI] += fabsf(d);                                                             \
+                        }
+                        BANET_CH(x, 0) BANET_CH(y, 1) BANET_CH(z, 2) BANET_CH(w, 3)
+#undef BANET_CH
+                    }
+                }
+                if (jc == NCH - 1) {
+                    m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
+                    if (hl == 0) {           // totals overwrite the tap offsets / n of this pixel's record (no longer needed)
+                        *reinterpret_cast<float4*>(rec + pl * REC) = make_float4(m11, m12, m22, q1);
+                        rec[pl * REC + 11] = q2;
+                    }
+                }
+            }
+            __syncwarp();
+            if (g == 0) TC6_TRACE(0, j, 2);
+            if (lane == 0) mbar_arrive(&gath[s]);
+        }
+        if (cur_b >= 0) dump_rb();
+    } else {
+        // ===================================================================== helper warps: geometry, algebra, R rows, drains
+        setmaxnreg_dec<72>();
+        const int hwi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*hwi .. 16*hwi+15, TMEM lanes 32*hwi .. +31
+        const int htid = tid - (W0 + GW) * 32;
+        const SlotLayout L{KB, C};
+        unsigned char* Rs = base + SM::off_R;
+        float* myPose = sPose + hwi * 32;
+        float cc[28];
+#pragma unroll
+        for (int q = 0; q < 28; ++q) cc[q] = 0.f;
+        int chain = -1, tic = 0, next_drain = 0;
+        bool first_drain = true;
+        int gpar = 1, geom_b = -1, spar = 1, scale_b = -1, sspan = -1;
+        TileCoord nxt = tile_coord(prm, t_begin);
+        int nxt_r = (int)((unsigned)t_begin - (unsigned)nxt.b * (unsigned)prm.tiles_per_pair);
+        const uint32_t offL = (lane >> 3) * 8192;            // this lane's 16-B chunk of a 128-float row: block lane>>3, chunk lane&7
+
+        auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
+            const int row = hwi * 32 + lane;
+            const uint32_t tq = tmem + ((uint32_t)(hwi * 32) << 16) + col0;
+            float v[32];
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                tmem_ld_32x32(tq + cb * 32, v);
+                float* dst = slot + (size_t)(cb * 32) * KB + row;
+                if (overwrite) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] = v[j];
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] += v[j];
+                }
+            }
+            tmem_ld_32x32(tq + 128, v);
+            float* dst = slot + L.off_ext() + row;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KB] = v[r]; else dst[r * KB] += v[r]; }
+        };
+        auto drain_hi = [&](int c, float* slot) {
+            const int set = c & 1;
+            mbar_wait(&chain_done[set], (c >> 1) & 1);
+            tc_fence_after_sync();
+            drain_region(slot, set * NN, first_drain);
+            first_drain = false;
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained[set]);
+        };
+        auto flush = [&](int sp) {
+            float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
+            for (; next_drain <= chain; ++next_drain) drain_hi(next_drain, slot);
+            mbar_wait(flushb, sp & 1);
+            tc_fence_after_sync();
+            if constexpr (MODE >= 2) drain_region(slot, ACCL, false);
+            tc_fence_before_sync();
+            // H_cc / g_c / nvalid partials of the 64 pixel-lanes through a scratch aliased on R (all MMAs of the span are done)
+            float* scratch = reinterpret_cast<float*>(base + SM::off_R);
+            if (lane < 16) {
+#pragma unroll
+                for (int q = 0; q < 28; ++q) scratch[(hwi * 16 + lane) * 28 + q] = cc[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 28; ++q) cc[q] = 0.f;
+            mbar_wait(rbdump, sp & 1);                       // the gather warps parked their |diff| sums for this pair
+            helper_bar<HW * 32>();
+            if (htid < C) {
+                float s = 0.f;
+#pragma unroll
+                for (int wq = 0; wq < GW; ++wq) s += sRbs[wq * 128 + htid];
+                slot[L.off_rbar() + htid] = s;
+            }
+            if (htid < 28) {
+                float s = 0.f;
+                for (int e = 0; e < TILE; ++e) s += scratch[e * 28 + htid];
+                slot[L.off_cc() + htid] = s;
+            }
+            helper_bar<HW * 32>();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(rbfree); mbar_arrive(tmemfree); }
+        };
+
+        // ---- geometry of tile j: records -> sRec[j%3], pair index -> sTile[j%3]
+        auto geom = [&](int j, int tj) {
+            const TileCoord tc = nxt;
+            if (++nxt_r == prm.tiles_per_pair) { nxt_r = 0; ++nxt.b; nxt.tx0 = 0; nxt.ty0 = 0; nxt.n0 = 0; nxt.cnt = grid2d ? TILE : min(TILE, N); }
+            else if (grid2d) { nxt.tx0 += 8; if (nxt.tx0 >= prm.tiles_x * 8) { nxt.tx0 = 0; nxt.ty0 += 8; } }
+            else { nxt.n0 += TILE; nxt.cnt = min(TILE, N - nxt.n0); }
+            const int b = tc.b;
+            if (b != geom_b) {
+                gpar ^= 1; geom_b = b;
+                float* pose = myPose + gpar * 16;
+                __syncwarp();
+                if (lane < 9) pose[lane] = prm.R[b * 9 + lane];
+                else if (lane < 12) pose[lane] = prm.T[b * 3 + lane - 9];
+                else if (lane < 16) pose[lane] = prm.intr[b * 4 + lane - 12];
+                *reinterpret_cast<float4*>(sW + gpar * 128 + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KB + 4 * lane));
+                __syncwarp();
+            }
+            const float* pose = myPose + gpar * 16;
+            const int s = j % 3, sr = j % NREC;
+            const unsigned char* As = base + SM::off_A + s * STAGE_A;
+            if (hwi == 0) TC6_TRACE(1, tj, 0);
+            mbar_wait(&fullB[s], (j / 3) & 1);
+            if (hwi == 0) TC6_TRACE(1, tj, 1);
+            // b.W: lane = (row lane&15, half lane>>4) walks 16 chunks of its row half, rotated so that a quarter-warp hits 8 distinct
+            // 16-B bank groups of the swizzled tile (and of W)
+            float mydot;
+            {
+                const int r = lane & 15, nl = hwi * 16 + r, hf = lane >> 4;
+                const float* wp = sW + gpar * 128;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r) & 7;
+                    const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nl, c));
+                    const float4 w4 = *reinterpret_cast<const float4*>(wp + blk * 32 + c * 4);
+                    acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
+                }
+                mydot = (acc.x + acc.y) + (acc.z + acc.w);
+                mydot += __shfl_xor_sync(0xffffffffu, mydot, 16);
+            }
+            if (hwi == 0) TC6_TRACE(1, tj, 2);
+            if (lane < 16) {                                 // thread per pixel (bundlenet.py:208-224, mask :231)
+                const int nl = hwi * 16 + lane;
+                int n; bool valid;
+                if (grid2d) { const int gx = tc.tx0 + (nl & 7), gy = tc.ty0 + (nl >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
+                else { valid = nl < tc.cnt; n = tc.n0 + nl; }
+                float mask = 0.f, x = 0.f, y = 0.f, iZ = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, dx = 0.f, dy = 0.f;
+                int x0 = 0, y0 = 0;
+                if (valid) {
+                    const float* pp = prm.p + (size_t)b * 3 * N + n;
+                    const float p0 = __ldg(pp), p1 = __ldg(pp + N), p2 = __ldg(pp + 2 * (size_t)N);
+                    const float Dt = __ldg(prm.D + (size_t)b * N + n) + mydot;
+                    rx = pose[0] * p0 + pose[1] * p1 + pose[2] * p2;
+                    ry = pose[3] * p0 + pose[4] * p1 + pose[5] * p2;
+                    rz = pose[6] * p0 + pose[7] * p1 + pose[8] * p2;
+                    const float X = rx * Dt + pose[9], Y = ry * Dt + pose[10], Z = rz * Dt + pose[11];
+                    x = X / Z; y = Y / Z; iZ = 1.0f / Z;
+                    const float u = pose[12] * x + pose[14], v = pose[13] * y + pose[15];
+                    if ((u >= 0.f) && (u <= (float)(w - 1)) && (v >= 0.f) && (v <= (float)(h - 1)) && isfinite(iZ)) {
+                        mask = 1.f;
+                        const float fu = floorf(u), fv = floorf(v);
+                        x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
+                    }
+                }
+                uint32_t o[4] = {(uint32_t)x0, (uint32_t)y0, 0u, 0u};
+                if constexpr (!FLY) {
+                    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+                    o[0] = (uint32_t)((y0 * w + x0) * c2); o[1] = (uint32_t)((y0 * w + x1) * c2);
+                    o[2] = (uint32_t)((y1 * w + x0) * c2); o[3] = (uint32_t)((y1 * w + x1) * c2);
+                }
+                float* rec = sRec + (sr * TILE + nl) * REC;
+                *reinterpret_cast<uint4*>(rec) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(rec + 4) = make_float4(mask, x, y, iZ);
+                *reinterpret_cast<float4*>(rec + 8) = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
+                *reinterpret_cast<float4*>(rec + 12) = make_float4(dx, dy, 0.f, 0.f);
+            }
+            if (hwi == 0 && lane == 0) sTile[sr * 4] = b;
+            __syncwarp();
+            if (hwi == 0) TC6_TRACE(1, tj, 3);
+            if (lane == 0) mbar_arrive(&recs[sr]);
+        };
+
+        // ---- algebra + R rows of tile j
+        auto s3scale = [&](int j, int b, bool last_of_pair) {
+            const int s = j % 3, sr = j % NREC;
+            if (b != scale_b) { spar ^= 1; scale_b = b; ++sspan; tic = 0; first_drain = true; }
+            const float* pose = myPose + spar * 16;
+            const unsigned char* As = base + SM::off_A + s * STAGE_A;
+            if (tic == 0) ++chain;
+            if (tic == CHAIN / 2 && next_drain < chain) {
+                drain_hi(next_drain, prm.partials + ((size_t)blockIdx.x * prm.max_span + sspan) * prm.slot_floats);
+                ++next_drain;
+            }
+            if (++tic == CHAIN) tic = 0;
+            if (hwi == 0) TC6_TRACE(1, j, 4);
+            mbar_wait(&gath[sr], (j / NREC) & 1);
+            if (hwi == 0) TC6_TRACE(1, j, 5);
+            if (lane < 16) {                                 // thread per pixel (bundlenet.py:49-74)
+                float* rec = sRec + (sr * TILE + hwi * 16 + lane) * REC;
+                const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
+                             rc = *reinterpret_cast<const float4*>(rec + 8);
+                float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (rbq.x != 0.f) {
+                    const float m11 = ra.x, m12 = ra.y, m22 = ra.z, q1 = ra.w, q2 = rc.w, x = rbq.y, y = rbq.z, iZ = rbq.w;
+                    const float rx = rc.x, ry = rc.y, rz = rc.z;
+                    const float fx = pose[12], fy = pose[13];
+                    const float a0[6] = {-fx * (x * y), -fx * (-1.f - x * x), -fx * y, -fx * (-iZ), 0.f, -fx * (x * iZ)};
+                    const float a1[6] = {-fy * (1.f + y * y), -fy * (-(x * y)), -fy * (-x), 0.f, -fy * (-iZ), -fy * (y * iZ)};
+                    float ux[6], uy[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) { ux[i] = m11 * a0[i] + m12 * a1[i]; uy[i] = m12 * a0[i] + m22 * a1[i]; }
+                    int q = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i)
+#pragma unroll
+                        for (int jj = i; jj < 6; ++jj) { cc[q] += a0[i] * ux[jj] + a1[i] * uy[jj]; ++q; }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) cc[21 + i] += a0[i] * q1 + a1[i] * q2;
+                    cc[27] += 1.f;
+                    const float jd0 = fx * ((rx - rz * x) * iZ), jd1 = fy * ((ry - rz * y) * iZ);
+                    const float u0 = m11 * jd0 + m12 * jd1, u1 = m12 * jd0 + m22 * jd1;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) ext[i] = a0[i] * u0 + a1[i] * u1;
+                    ext[6] = jd0 * q1 + jd1 * q2;
+                    ext[7] = jd0 * u0 + jd1 * u1;
+                }
+                *reinterpret_cast<float4*>(rec) = make_float4(ext[0], ext[1], ext[2], ext[3]);
+                *reinterpret_cast<float4*>(rec + 4) = make_float4(ext[4], ext[5], ext[6], ext[7]);
+            }
+            __syncwarp();
+            if (hwi == 0) TC6_TRACE(1, j, 6);
+            if (j > 0) mbar_wait(rfree, (j - 1) & 1);
+            if (hwi == 0) TC6_TRACE(1, j, 7);
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {                   // warp per row: lanes over the 128 basis columns (conflict-free float4)
+                const int nl = hwi * 16 + i;
+                const float* rec = sRec + (sr * TILE + nl) * REC;
+                const float sn = rec[7];
+                const uint32_t off = offL + sw128_32b_off(nl, lane & 7);
+                const float4 bv = *reinterpret_cast<const float4*>(As + off);
+                const float4 pv = make_float4(sn * bv.x, sn * bv.y, sn * bv.z, sn * bv.w);
+                const float4 hv = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
+                *reinterpret_cast<float4*>(Rs + off) = hv;
+                if constexpr (MODE >= 2)
+                    *reinterpret_cast<float4*>(base + SM::off_Alo + off) = make_float4(bv.x - tf32_trunc(bv.x), bv.y - tf32_trunc(bv.y), bv.z - tf32_trunc(bv.z), bv.w - tf32_trunc(bv.w));
+                if constexpr (MODE == 3)
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + off) = make_float4(pv.x - hv.x, pv.y - hv.y, pv.z - hv.z, pv.w - hv.w);
+                if (lane < 2) {
+                    float4 ev = *reinterpret_cast<const float4*>(rec + 4 * lane);
+                    if (lane == 1) ev.w = 0.f;
+                    const float4 eh = make_float4(tf32_rna(ev.x), tf32_rna(ev.y), tf32_rna(ev.z), tf32_rna(ev.w));
+                    const uint32_t offE = 4 * 8192 + sw128_32b_off(nl, lane);
+                    *reinterpret_cast<float4*>(Rs + offE) = eh;
+                    if constexpr (MODE == 3)
+                        *reinterpret_cast<float4*>(base + SM::off_Rlo + offE) = make_float4(ev.x - eh.x, ev.y - eh.y, ev.z - eh.z, ev.w - eh.w);
+                }
+            }
+            if (hwi == 0) TC6_TRACE(1, j, 8);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (hwi == 0) TC6_TRACE(1, j, 9);
+            if (lane == 0) mbar_arrive(ready);
+            if (last_of_pair) flush(sspan);
+        };
+
+        if (ntiles > 0) geom(0, -1);
+        int b_cur = (ntiles > 0) ? tile_coord(prm, t_begin).b : -1;
+        for (int j = 0; j < ntiles; ++j) {
+            int b_next = -1;
+            if (j + 1 < ntiles) { b_next = nxt.b; geom(j + 1, j); }
+            s3scale(j, b_cur, b_next != b_cur);
+            b_cur = b_next;
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
+}
+
+template <int NCH, bool FLY, int MODE>
+static int launch6(const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+{
+    auto kern = lm_build_tc6_kernel<NCH, FLY, MODE>;
+    const int smem = Smem<MODE>::bytes;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("lm_build_tc6: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return BANET_ERR_CUDA; }
+    kern<<<grid, THREADS, smem, st>>>(tm, prm);
+    BANET_CUDA_LAUNCH_CHECK("lm_build_tc6_kernel launch");
+    return BANET_OK;
+}
+template <int NCH, bool FLY>
+static int launch6_mode(int mode, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+{
+    if (mode == 1) return launch6<NCH, FLY, 1>(tm, prm, grid, st);
+    if (mode == 2) return launch6<NCH, FLY, 2>(tm, prm, grid, st);
+    return launch6<NCH, FLY, 3>(tm, prm, grid, st);
+}
+
+}  // namespace v6
+
+int lm_build_tc6_launch(int mode, bool fly, int nch, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+{
+    if (nch == 2) return fly ? v6::launch6_mode<2, true>(mode, tm, prm, grid, st) : v6::launch6_mode<2, false>(mode, tm, prm, grid, st);
+    return fly ? v6::launch6_mode<1, true>(mode, tm, prm, grid, st) : v6::launch6_mode<1, false>(mode, tm, prm, grid, st);
+}
+
+}  // namespace banet
