@@ -20,8 +20,8 @@
 namespace banet { namespace v6 {
 using namespace tc;
 
-constexpr int TILE = 64, GW = 16, HW = 4, W0 = 4;
-constexpr int THREADS = (W0 + GW + HW) * 32;          // 768
+constexpr int TILE = 64, GW = 16, HW = 4, DW = 4, W0 = 4;
+constexpr int THREADS = (W0 + GW + HW + DW) * 32;     // 896
 constexpr int KB = 128, NN = 160;
 constexpr int STAGE_A = 4 * TILE * 128, STAGE_R = 5 * TILE * 128;
 constexpr int REC = 16, NREC = 2;     // record buffers: geometry of tile j+1 overlaps gather / algebra of tile j
@@ -40,7 +40,8 @@ template <int MODE> struct Smem {
     static constexpr int off_w = off_pose + HW * 2 * 16 * 4;          // [2 parities][128] floats: W of the pair (identical writes by every helper warp)
     static constexpr int off_rec = off_w + 2 * 128 * 4;         // [NREC][TILE][REC] floats
     static constexpr int off_rbs = off_rec + NREC * TILE * REC * 4;       // [GW][128] floats: rbar hand-over gather -> helpers
-    static constexpr int total = off_rbs + GW * 128 * 4;
+    static constexpr int off_ccs = off_rbs + GW * 128 * 4;            // [HW][28] floats: H_cc / g_c / nvalid partials per helper warp
+    static constexpr int total = off_ccs + HW * 28 * 4;
     static constexpr int bytes = total + 512;
 };
 
@@ -98,6 +99,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
     float* sW = reinterpret_cast<float*>(base + SM::off_w);
     float* sRec = reinterpret_cast<float*>(base + SM::off_rec);
     float* sRbs = reinterpret_cast<float*>(base + SM::off_rbs);
+    float* sCcs = reinterpret_cast<float*>(base + SM::off_ccs);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int N = prm.N, h = prm.h, w = prm.w, c2 = prm.c2;
@@ -109,8 +111,8 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
 
     if (tid == 0) {
         for (int i = 0; i < 3; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); mbar_init(&recs[i], HW); mbar_init(&gath[i], GW); }
-        mbar_init(ready, HW); mbar_init(rfree, 1); mbar_init(flushb, 1); mbar_init(tmemfree, HW);
-        mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1); mbar_init(&drained[0], HW); mbar_init(&drained[1], HW);
+        mbar_init(ready, HW); mbar_init(rfree, 1); mbar_init(flushb, 1); mbar_init(tmemfree, DW);
+        mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1); mbar_init(&drained[0], DW); mbar_init(&drained[1], DW);
         mbar_init(rbdump, GW); mbar_init(rbfree, HW);
         fence_barrier_init();
         prefetch_tmap(&tmapB);
@@ -222,7 +224,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
       }
     } else if (warp < W0 + GW) {
         // ===================================================================== gather warps: records -> taps -> M, q
-        setmaxnreg_inc<96>();
+        setmaxnreg_inc<88>();
         const int g = warp - W0, hw = lane >> 4, hl = lane & 15;
         constexpr int PXW = TILE / GW;                       // 4 pixels per warp and tile
         constexpr int NUNIT = (PXW / 2) * NCH;
@@ -335,7 +337,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             if (lane == 0) mbar_arrive(&gath[s]);
         }
         if (cur_b >= 0) dump_rb();
-    } else {
+    } else if (warp < W0 + GW + HW) {
         // ===================================================================== helper warps: geometry, algebra, R rows, drains
         setmaxnreg_dec<72>();
         const int hwi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*hwi .. 16*hwi+15, TMEM lanes 32*hwi .. +31
@@ -346,59 +348,21 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         float cc[28];
 #pragma unroll
         for (int q = 0; q < 28; ++q) cc[q] = 0.f;
-        int chain = -1, tic = 0, next_drain = 0;
-        bool first_drain = true;
         int gpar = 1, geom_b = -1, spar = 1, scale_b = -1, sspan = -1;
         TileCoord nxt = tile_coord(prm, t_begin);
         int nxt_r = (int)((unsigned)t_begin - (unsigned)nxt.b * (unsigned)prm.tiles_per_pair);
-        const uint32_t offL = (lane >> 3) * 8192;            // this lane's 16-B chunk of a 128-float row: block lane>>3, chunk lane&7
 
-        auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
-            const int row = hwi * 32 + lane;
-            const uint32_t tq = tmem + ((uint32_t)(hwi * 32) << 16) + col0;
-            float v[32];
-#pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                tmem_ld_32x32(tq + cb * 32, v);
-                float* dst = slot + (size_t)(cb * 32) * KB + row;
-                if (overwrite) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] = v[j];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] += v[j];
-                }
-            }
-            tmem_ld_32x32(tq + 128, v);
-            float* dst = slot + L.off_ext() + row;
-#pragma unroll
-            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KB] = v[r]; else dst[r * KB] += v[r]; }
-        };
-        auto drain_hi = [&](int c, float* slot) {
-            const int set = c & 1;
-            mbar_wait(&chain_done[set], (c >> 1) & 1);
-            tc_fence_after_sync();
-            drain_region(slot, set * NN, first_drain);
-            first_drain = false;
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&drained[set]);
-        };
         auto flush = [&](int sp) {
             float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
-            for (; next_drain <= chain; ++next_drain) drain_hi(next_drain, slot);
-            mbar_wait(flushb, sp & 1);
-            tc_fence_after_sync();
-            if constexpr (MODE >= 2) drain_region(slot, ACCL, false);
-            tc_fence_before_sync();
-            // H_cc / g_c / nvalid partials of the 64 pixel-lanes through a scratch aliased on R (all MMAs of the span are done)
-            float* scratch = reinterpret_cast<float*>(base + SM::off_R);
-            if (lane < 16) {
+            // H_cc / g_c / nvalid: 16 pixel-lanes -> warp total (fixed shuffle tree) -> 4 warp partials summed in fixed order
 #pragma unroll
-                for (int q = 0; q < 28; ++q) scratch[(hwi * 16 + lane) * 28 + q] = cc[q];
+            for (int q = 0; q < 28; ++q) {
+                float v = cc[q];
+                v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (lane == 0) sCcs[hwi * 28 + q] = v;
+                cc[q] = 0.f;
             }
-#pragma unroll
-            for (int q = 0; q < 28; ++q) cc[q] = 0.f;
             mbar_wait(rbdump, sp & 1);                       // the gather warps parked their |diff| sums for this pair
             helper_bar<HW * 32>();
             if (htid < C) {
@@ -407,14 +371,9 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 for (int wq = 0; wq < GW; ++wq) s += sRbs[wq * 128 + htid];
                 slot[L.off_rbar() + htid] = s;
             }
-            if (htid < 28) {
-                float s = 0.f;
-                for (int e = 0; e < TILE; ++e) s += scratch[e * 28 + htid];
-                slot[L.off_cc() + htid] = s;
-            }
+            if (htid < 28) slot[L.off_cc() + htid] = (sCcs[htid] + sCcs[28 + htid]) + (sCcs[56 + htid] + sCcs[84 + htid]);
             helper_bar<HW * 32>();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(rbfree); mbar_arrive(tmemfree); }
+            if (lane == 0) mbar_arrive(rbfree);
         };
 
         // ---- geometry of tile j: records -> sRec[j%3], pair index -> sTile[j%3]
@@ -502,23 +461,17 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         // ---- algebra + R rows of tile j
         auto s3scale = [&](int j, int b, bool last_of_pair) {
             const int s = j % 3, sr = j % NREC;
-            if (b != scale_b) { spar ^= 1; scale_b = b; ++sspan; tic = 0; first_drain = true; }
+            if (b != scale_b) { spar ^= 1; scale_b = b; ++sspan; }
             const float* pose = myPose + spar * 16;
             const unsigned char* As = base + SM::off_A + s * STAGE_A;
-            if (tic == 0) ++chain;
-            if (tic == CHAIN / 2 && next_drain < chain) {
-                drain_hi(next_drain, prm.partials + ((size_t)blockIdx.x * prm.max_span + sspan) * prm.slot_floats);
-                ++next_drain;
-            }
-            if (++tic == CHAIN) tic = 0;
             if (hwi == 0) TC6_TRACE(1, j, 4);
             mbar_wait(&gath[sr], (j / NREC) & 1);
             if (hwi == 0) TC6_TRACE(1, j, 5);
+            float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (lane < 16) {                                 // thread per pixel (bundlenet.py:49-74)
-                float* rec = sRec + (sr * TILE + hwi * 16 + lane) * REC;
+                const float* rec = sRec + (sr * TILE + hwi * 16 + lane) * REC;
                 const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
                              rc = *reinterpret_cast<const float4*>(rec + 8);
-                float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (rbq.x != 0.f) {
                     const float m11 = ra.x, m12 = ra.y, m22 = ra.z, q1 = ra.w, q2 = rc.w, x = rbq.y, y = rbq.z, iZ = rbq.w;
                     const float rx = rc.x, ry = rc.y, rz = rc.z;
@@ -543,19 +496,27 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     ext[6] = jd0 * q1 + jd1 * q2;
                     ext[7] = jd0 * u0 + jd1 * u1;
                 }
-                *reinterpret_cast<float4*>(rec) = make_float4(ext[0], ext[1], ext[2], ext[3]);
-                *reinterpret_cast<float4*>(rec + 4) = make_float4(ext[4], ext[5], ext[6], ext[7]);
             }
-            __syncwarp();
+            const int r = lane & 15, nl = hwi * 16 + r, hf = lane >> 4;
+            const float sn = __shfl_sync(0xffffffffu, ext[7], r);     // s_n of this lane's row
             if (hwi == 0) TC6_TRACE(1, j, 6);
             if (j > 0) mbar_wait(rfree, (j - 1) & 1);
             if (hwi == 0) TC6_TRACE(1, j, 7);
-#pragma unroll 4
-            for (int i = 0; i < 16; ++i) {                   // warp per row: lanes over the 128 basis columns (conflict-free float4)
-                const int nl = hwi * 16 + i;
-                const float* rec = sRec + (sr * TILE + nl) * REC;
-                const float sn = rec[7];
-                const uint32_t off = offL + sw128_32b_off(nl, lane & 7);
+            if (lane < 16) {                                 // R columns 128..134 = [v(6) | t], column 135 stays zero
+                const float4 e0 = make_float4(tf32_rna(ext[0]), tf32_rna(ext[1]), tf32_rna(ext[2]), tf32_rna(ext[3]));
+                const float4 e1 = make_float4(tf32_rna(ext[4]), tf32_rna(ext[5]), tf32_rna(ext[6]), 0.f);
+                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 0)) = e0;
+                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 1)) = e1;
+                if constexpr (MODE == 3) {
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nl, 0)) = make_float4(ext[0] - e0.x, ext[1] - e0.y, ext[2] - e0.z, ext[3] - e0.w);
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nl, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
+                }
+            }
+            // R rows: lane = (row lane&15, half lane>>4) walks the 16 chunks of its half row (rotated: conflict-free quarter-warps)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r) & 7;
+                const uint32_t off = blk * 8192 + sw128_32b_off(nl, c);
                 const float4 bv = *reinterpret_cast<const float4*>(As + off);
                 const float4 pv = make_float4(sn * bv.x, sn * bv.y, sn * bv.z, sn * bv.w);
                 const float4 hv = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
@@ -564,15 +525,6 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     *reinterpret_cast<float4*>(base + SM::off_Alo + off) = make_float4(bv.x - tf32_trunc(bv.x), bv.y - tf32_trunc(bv.y), bv.z - tf32_trunc(bv.z), bv.w - tf32_trunc(bv.w));
                 if constexpr (MODE == 3)
                     *reinterpret_cast<float4*>(base + SM::off_Rlo + off) = make_float4(pv.x - hv.x, pv.y - hv.y, pv.z - hv.z, pv.w - hv.w);
-                if (lane < 2) {
-                    float4 ev = *reinterpret_cast<const float4*>(rec + 4 * lane);
-                    if (lane == 1) ev.w = 0.f;
-                    const float4 eh = make_float4(tf32_rna(ev.x), tf32_rna(ev.y), tf32_rna(ev.z), tf32_rna(ev.w));
-                    const uint32_t offE = 4 * 8192 + sw128_32b_off(nl, lane);
-                    *reinterpret_cast<float4*>(Rs + offE) = eh;
-                    if constexpr (MODE == 3)
-                        *reinterpret_cast<float4*>(base + SM::off_Rlo + offE) = make_float4(ev.x - eh.x, ev.y - eh.y, ev.z - eh.z, ev.w - eh.w);
-                }
             }
             if (hwi == 0) TC6_TRACE(1, j, 8);
             fence_proxy_async_smem();
@@ -590,6 +542,73 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             s3scale(j, b_cur, b_next != b_cur);
             b_cur = b_next;
         }
+    } else {
+        // ===================================================================== drainer warps: TMEM -> partial slots, fully asynchronous
+        setmaxnreg_dec<56>();
+        const int dq = warp - (W0 + GW + HW);                // TMEM lane quadrant (= warp % 4)
+        const SlotLayout L{KB, C};
+        auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
+            const int row = dq * 32 + lane;
+            const uint32_t tq = tmem + ((uint32_t)(dq * 32) << 16) + col0;
+            float v[32];
+#pragma unroll 1
+            for (int cb = 0; cb < 4; ++cb) {
+                tmem_ld_32x32(tq + cb * 32, v);
+                float* dst = slot + (size_t)(cb * 32) * KB + row;
+                if (overwrite) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] = v[j];
+                } else {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float o[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)(16 * hh + j) * KB];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) dst[(size_t)(16 * hh + j) * KB] = o[j] + v[16 * hh + j];
+                    }
+                }
+            }
+            tmem_ld_32x32(tq + 128, v);
+            float* dst = slot + L.off_ext() + row;
+#pragma unroll
+            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KB] = v[r]; else dst[r * KB] += v[r]; }
+        };
+        int chain = -1, tic = 0, span = 0, cur_b = -1;
+        bool first = true;
+        int b = (ntiles > 0) ? (int)((unsigned)t_begin / (unsigned)prm.tiles_per_pair) : 0;
+        int rr = (ntiles > 0) ? (int)((unsigned)t_begin - (unsigned)b * (unsigned)prm.tiles_per_pair) : 0;
+        auto drain_hi = [&]() {
+            const int set = chain & 1;
+            float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats;
+            mbar_wait_sleep(&chain_done[set], (chain >> 1) & 1);
+            tc_fence_after_sync();
+            drain_region(slot, set * NN, first);
+            first = false;
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&drained[set]);
+        };
+        auto end_span = [&]() {
+            if (tic > 0) drain_hi();
+            if constexpr (MODE >= 2) {
+                float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats;
+                mbar_wait_sleep(flushb, span & 1);
+                tc_fence_after_sync();
+                drain_region(slot, ACCL, false);
+                tc_fence_before_sync();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmemfree);
+            ++span;
+        };
+        for (int it = 0; it < ntiles; ++it) {
+            if (b != cur_b) { if (cur_b >= 0) end_span(); cur_b = b; tic = 0; first = true; }
+            if (tic == 0) ++chain;
+            if (++tic == CHAIN) { drain_hi(); tic = 0; }
+            if (++rr == prm.tiles_per_pair) { rr = 0; ++b; }
+        }
+        if (cur_b >= 0) end_span();
     }
 
     tc_fence_before_sync();
