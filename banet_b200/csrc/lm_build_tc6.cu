@@ -1,16 +1,17 @@
-// lm_build_tc6.cu — tensor-core build kernel, generation 6: the per-pixel scalar phases move to a helper warpgroup.
+// lm_build_tc6.cu — tensor-core build kernel, generation 6: every phase has its own warpgroup, phases of different tiles overlap.
 //
-// Same contract, slot layout and precision modes as lm_build_tc.cu (read its header first).  What changes is WHO does what:
+// Same contract, slot layout and precision modes as lm_build_tc.cu (read its header first).  Roles (896 threads, 1 CTA / SM):
 //
-//   warpgroup 0   warp 0 TMA producer | warp 1 tcgen05.mma issuer | warp 2 L2 prefetcher | warp 3 idle      (24 regs)
-//   warpgroups 1-4  16 gather warps, 4 pixels each per tile: ONLY  records -> 13 tap loads -> blend/accumulate -> M,q   (96 regs)
-//   warpgroup 5   4 helper warps, 16 pixels each per tile, full lane efficiency:                               (72 regs)
-//                   geometry of tile j+1 : b.W (warp per pixel), warp / mask / tap offsets (thread per pixel) -> records
-//                   algebra of tile j    : 2x7 per-pixel algebra (thread per pixel, H_cc/g_c partials in registers),
-//                                          R rows (A_lo, R_lo) (warp per row, lanes over the 128 basis columns) -> MMA
-//                   TMEM drains (one lane quadrant per helper warp), slot publication
-//   mbarriers: recs[3] helpers->gather (records of tile j ready), gath[3] gather->helpers (M,q of tile j written);
-//   everything else (fullB/emptyB/ready/rfree/chain_done/drained/flushb/tmemfree) as in generation 5.
+//   warpgroup 0    4 geometry warps, 16 pixels each per tile, run ahead of everybody:                              (48 regs)
+//                    b.W from the TMA-staged basis tile, warp / mask / tap offsets -> pixel records (ring of NREC)
+//   warpgroups 1-4 16 gather warps, 4 pixels each per tile: records -> 13 tap loads -> blend / accumulate -> M, q  (88 regs)
+//   warpgroup 5    4 algebra warps, 16 pixels each per tile:                                                        (64 regs)
+//                    2x7 per-pixel algebra (H_cc / g_c partials in registers), R rows (A_lo, R_lo) into smem,
+//                    then ONE elected thread issues the tile's tcgen05.mma and refills the freed basis stage by TMA
+//   warpgroup 6    4 drainer warps (one TMEM lane quadrant each): TMEM chains -> partial slots, fully asynchronous  (40 regs)
+//   mbarriers: fullB[NST] TMA landed | recs[NREC] geometry->gather | gath[NREC] gather->algebra | recfree[NREC] algebra->geometry |
+//              rfree MMAs of the tile done (R, A_lo and the A stage reusable) | chain_done/drained[2], flushb, tmemfree issuer<->drainers |
+//              rbdump/rbfree gather<->algebra hand-over of the |diff| sums at a pair change.
 #include "common.cuh"
 #include "lm_build.h"
 #include "tc_utils.cuh"
@@ -20,29 +21,42 @@
 namespace banet { namespace v6 {
 using namespace tc;
 
-constexpr int TILE = 64, GW = 16, HW = 4, DW = 4, W0 = 4;
-constexpr int THREADS = (W0 + GW + HW + DW) * 32;     // 896
+constexpr int TILE = 64, W0 = 4, GW = 16, AW = 4, DW = 4;      // geometry | gather | algebra | drainer warps
+constexpr int THREADS = (W0 + GW + AW + DW) * 32;               // 896
 constexpr int KB = 128, NN = 160;
 constexpr int STAGE_A = 4 * TILE * 128, STAGE_R = 5 * TILE * 128;
-constexpr int REC = 16, NREC = 2;     // record buffers: geometry of tile j+1 overlaps gather / algebra of tile j
+constexpr int REC = 16;
 constexpr int CHAIN = 8, TMEM_COLS = 512, ACCL = 320;
 
-template <int MODE> struct Smem {
-    static constexpr int off_A = 0;                                    // 3 stages
-    static constexpr int off_R = 3 * STAGE_A;
+template <int MODE, bool FLY> struct Smem {
+#ifndef BANET_TC6_NST
+#define BANET_TC6_NST 4
+#endif
+#ifndef BANET_TC6_NREC
+#define BANET_TC6_NREC 3
+#endif
+    // basis-tile stages (TMA ring) and pixel-record buffers.  Deeper rings decouple the roles, but whatever smem the CTA takes is lost
+    // to the L1 that catches the tap overlap of neighbouring pixels: measured best per mode / layout (640x480, 32 pairs):
+    //   TF32X2 + [F2|gx|gy] layout: 3 stages (192 KB -> 196 KB carve-out, 60 KB L1) 7.4 ms vs 4 stages (228 KB) 8.6 ms
+    //   TF32X2 + F2-only layout   : 4 stages 7.2 ms vs 3 stages 8.8 ms;  TF32X1: 4 stages 5.6 ms vs 3 stages 6.1 ms
+    static constexpr int NST = MODE == 3 ? 3 : (MODE == 2 && !FLY) ? 3 : BANET_TC6_NST;
+    static constexpr int NREC = MODE == 3 ? 2 : BANET_TC6_NREC;
+    static constexpr int off_A = 0;
+    static constexpr int off_R = NST * STAGE_A;
     static constexpr int off_Alo = off_R + STAGE_R;
     static constexpr int off_Rlo = off_Alo + (MODE >= 2 ? STAGE_A : 0);
     static constexpr int off_misc = off_Rlo + (MODE == 3 ? STAGE_R : 0);
     static constexpr int off_bar = off_misc;                           // 22 mbarriers
     static constexpr int off_tmem = off_bar + 22 * 8;
     static constexpr int off_tile = off_misc + 192;                    // [NREC][4] ints: pair index of the tile in record buffer s
-    static constexpr int off_pose = off_tile + 64;                     // [HW][2 parities][16] floats
-    static constexpr int off_w = off_pose + HW * 2 * 16 * 4;          // [2 parities][128] floats: W of the pair (identical writes by every helper warp)
-    static constexpr int off_rec = off_w + 2 * 128 * 4;         // [NREC][TILE][REC] floats
-    static constexpr int off_rbs = off_rec + NREC * TILE * REC * 4;       // [GW][128] floats: rbar hand-over gather -> helpers
-    static constexpr int off_ccs = off_rbs + GW * 128 * 4;            // [HW][28] floats: H_cc / g_c / nvalid partials per helper warp
-    static constexpr int total = off_ccs + HW * 28 * 4;
-    static constexpr int bytes = total + 512;
+    static constexpr int off_pose = off_tile + 64;                     // [W0][16] floats (private to each geometry warp)
+    static constexpr int off_w = off_pose + W0 * 16 * 4;               // [W0][128] floats: W of the pair (private to each geometry warp)
+    static constexpr int off_rec = off_w + W0 * 128 * 4;               // [NREC][TILE][REC] floats
+    static constexpr int off_rbs = off_rec + NREC * TILE * REC * 4;    // [GW][128] floats: rbar hand-over gather -> algebra
+    static constexpr int off_ccs = off_rbs + GW * 128 * 4;             // [AW][28] floats: H_cc / g_c / nvalid partials per algebra warp
+    static constexpr int total = off_ccs + AW * 28 * 4;
+    static constexpr int slack = MODE == 3 ? 0 : 512;                  // MODE 3 fills the SM: the (512-B) base alignment is checked, not padded
+    static constexpr int bytes = total + slack;
 };
 
 __device__ __forceinline__ long long gtime6() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -76,23 +90,24 @@ template <int NCH, bool FLY, int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
 lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams prm)
 {
-    using SM = Smem<MODE>;
+    using SM = Smem<MODE, FLY>;
+    constexpr int NST = SM::NST, NREC = SM::NREC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align through the 32-bit shared address so that the compiler keeps every access in the shared state space (LDS/STS, not generic LD/ST)
-    unsigned char* base = smem_raw + ((512u - (smem_u32(smem_raw) & 511u)) & 511u);
+    unsigned char* base = smem_raw + (SM::slack ? ((512u - (smem_u32(smem_raw) & 511u)) & 511u) : 0u);
+    if (SM::slack == 0 && (smem_u32(smem_raw) & 511u)) __trap();      // fail loudly: swizzle atoms need 512-B aligned stage bases
     uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::off_bar);
-    uint64_t* fullB = bars;            // [3] TMA landed
-    uint64_t* emptyB = bars + 3;       // [3] MMAs reading A stage s completed
-    uint64_t* ready = bars + 6;        //     R (Alo,Rlo) of the tile written by the 4 helper warps
-    uint64_t* rfree = bars + 7;        //     MMAs of the tile completed
-    uint64_t* flushb = bars + 8;       //     every MMA of the span completed
-    uint64_t* tmemfree = bars + 9;     //     lo accumulator drained
-    uint64_t* chain_done = bars + 10;  // [2]
-    uint64_t* drained = bars + 12;     // [2]
-    uint64_t* recs = bars + 14;        // [NREC] records of the tile in buffer s written (count HW)
-    uint64_t* gath = bars + 17;        // [NREC] M,q of the tile in buffer s written (count GW)
-    uint64_t* rbdump = bars + 20;      //     gather warps parked their rbar partials (count GW)
-    uint64_t* rbfree = bars + 21;      //     helpers consumed them (count HW)
+    uint64_t* fullB = bars;            // [NST]  TMA landed
+    uint64_t* rfree = bars + 4;        //        MMAs of the tile completed
+    uint64_t* flushb = bars + 5;       //        every MMA of the span completed
+    uint64_t* tmemfree = bars + 6;     //        lo accumulator drained
+    uint64_t* chain_done = bars + 7;   // [2]
+    uint64_t* drained = bars + 9;      // [2]
+    uint64_t* recs = bars + 11;        // [NREC] records of the tile in buffer s written (count W0)
+    uint64_t* gath = bars + 14;        // [NREC] M,q of the tile in buffer s written (count GW)
+    uint64_t* recfree = bars + 17;     // [NREC] records of the tile in buffer s consumed by the algebra warps (count AW)
+    uint64_t* rbdump = bars + 20;      //        gather warps parked their rbar partials (count GW)
+    uint64_t* rbfree = bars + 21;      //        algebra warps consumed them (count AW)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(base + SM::off_tmem);
     int* sTile = reinterpret_cast<int*>(base + SM::off_tile);
     float* sPose = reinterpret_cast<float*>(base + SM::off_pose);
@@ -110,10 +125,11 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
     const int ntiles = (int)(t_end - t_begin);
 
     if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); mbar_init(&recs[i], HW); mbar_init(&gath[i], GW); }
-        mbar_init(ready, HW); mbar_init(rfree, 1); mbar_init(flushb, 1); mbar_init(tmemfree, DW);
+        for (int i = 0; i < NST; ++i) mbar_init(&fullB[i], 1);
+        for (int i = 0; i < NREC; ++i) { mbar_init(&recs[i], W0); mbar_init(&gath[i], GW); mbar_init(&recfree[i], AW); }
+        mbar_init(rfree, 1); mbar_init(flushb, 1); mbar_init(tmemfree, DW);
         mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1); mbar_init(&drained[0], DW); mbar_init(&drained[1], DW);
-        mbar_init(rbdump, GW); mbar_init(rbfree, HW);
+        mbar_init(rbdump, GW); mbar_init(rbfree, AW);
         fence_barrier_init();
         prefetch_tmap(&tmapB);
     }
@@ -129,99 +145,134 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
     tc_fence_after_sync();
     const uint32_t tmem = *s_tmem;
 
+    // lane -> (row r of the warp's 16, half hf of the 128 basis columns); 16-B chunk walk rotated by the row so that every
+    // quarter-warp touches 8 distinct bank groups of the swizzled tile (used by the b.W and the R-row loops)
+    const int r16 = lane & 15, hf = lane >> 4;
+
     if (warp < W0) {
-      setmaxnreg_dec<24>();
-      if (warp == 0) {
-        // ===================================================================== TMA producer
-        if (lane == 0) {
-            int it = 0;
-            for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it % 3, ph = (it / 3) & 1;
-                const TileCoord tc = tile_coord(prm, t);
-                mbar_wait_sleep(&emptyB[s], ph ^ 1);
-                mbar_arrive_expect_tx(&fullB[s], STAGE_A);
-                unsigned char* dst = base + SM::off_A + s * STAGE_A;
+        // ===================================================================== geometry warps: b.W, warp, mask, tap offsets -> records
+        setmaxnreg_dec<48>();
+        const int gwi = warp, nlr = gwi * 16 + r16;
+        float* myPose = sPose + gwi * 16;
+        float* myW = sW + gwi * 128;
+        int geom_b = -1;
+        TileCoord nxt = tile_coord(prm, t_begin);
+        int nxt_r = (int)((unsigned)t_begin - (unsigned)nxt.b * (unsigned)prm.tiles_per_pair);
+        for (int j = 0; j < ntiles; ++j) {
+            const TileCoord tc = nxt;
+            if (++nxt_r == prm.tiles_per_pair) { nxt_r = 0; ++nxt.b; nxt.tx0 = 0; nxt.ty0 = 0; nxt.n0 = 0; nxt.cnt = grid2d ? TILE : min(TILE, N); }
+            else if (grid2d) { nxt.tx0 += 8; if (nxt.tx0 >= prm.tiles_x * 8) { nxt.tx0 = 0; nxt.ty0 += 8; } }
+            else { nxt.n0 += TILE; nxt.cnt = min(TILE, N - nxt.n0); }
+            const int b = tc.b;
+            if (gwi == 1 && j + 2 < ntiles) {             // L2 prefetch of the streaming inputs (conv1, p, D) two tiles ahead
+                const TileCoord tn = tile_coord(prm, t_begin + j + 2);
                 if (grid2d) {
+                    if (lane < 8) {
+                        const int gy = tn.ty0 + lane;
+                        if (gy < prm.grid_h && tn.tx0 < prm.grid_w) {
+                            const size_t n = (size_t)gy * prm.grid_w + tn.tx0;
+                            const int wpx = min(8, prm.grid_w - tn.tx0);
+                            prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + n) * C, (uint32_t)(wpx * C * 4));
+                            if ((n & 3) == 0 && (N & 3) == 0) {
+                                const uint32_t by = (uint32_t)(((wpx * 4) + 15) & ~15);
+                                prefetch_l2_bulk(prm.D + (size_t)tn.b * N + n, by);
 #pragma unroll
-                    for (int blk = 0; blk < 4; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[s]);
-                } else {
-                    const int row = tc.b * N + tc.n0;
-#pragma unroll
-                    for (int blk = 0; blk < 4; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[s]);
-                }
-            }
-        }
-      } else if (warp == 1) {
-        // ===================================================================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, NN);
-            int it = 0, span = 0, cur_b = -1, chain = -1, tic = 0, set = 0;
-            uint32_t accH = 0, accL = 0;
-            const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
-            for (long long t = t_begin; t < t_end; ++t, ++it) {
-                const int s = it % 3;
-                const int b = (int)((unsigned)t / (unsigned)prm.tiles_per_pair);
-                if (b != cur_b) {
-                    if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++span; }
-                    mbar_wait_sleep(tmemfree, (span & 1) ^ 1);
-                    accL = 0; cur_b = b; tic = 0;
-                }
-                if (tic == 0) { ++chain; set = chain & 1; mbar_wait_sleep(&drained[set], ((chain >> 1) & 1) ^ 1); accH = 0; }
-                mbar_wait_sleep(ready, it & 1);
-                tc_fence_after_sync();
-                const uint32_t ahi = smem_u32(base + SM::off_A + s * STAGE_A);
-#pragma unroll
-                for (int pass = 0; pass < MODE; ++pass) {
-                    const uint32_t a0 = (pass == 1) ? alo : ahi;
-                    const uint32_t r0 = (pass == 2) ? rlo : rhi;
-                    const uint32_t dcol = tmem + (pass == 0 ? set * NN : ACCL);
-#pragma unroll
-                    for (int kk = 0; kk < TILE / 8; ++kk) {
-                        mma_tf32_ss(dcol, make_desc_mn_sw128_32b(a0 + kk * 1024, 8192, 512),
-                                    make_desc_mn_sw128_32b(r0 + kk * 1024, 8192, 512), idesc, pass == 0 ? accH : accL);
-                        if (pass == 0) accH = 1; else accL = 1;
-                    }
-                }
-                mma_commit(&emptyB[s]);
-                mma_commit(rfree);
-                if (++tic == CHAIN) { mma_commit(&chain_done[set]); tic = 0; }
-            }
-            if (cur_b >= 0) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); }
-        }
-      } else if (warp == 2) {
-        // ===================================================================== L2 prefetcher of the streaming inputs (conv1, p, D)
-        int it = 0;
-        for (long long t = t_begin; t < t_end; ++t, ++it) {
-            const long long tp = t + 2;
-            if (tp >= t_end) break;
-            mbar_wait_bounded(&fullB[it % 3], (it / 3) & 1, 4000);      // pacing only (best effort)
-            const TileCoord tn = tile_coord(prm, tp);
-            if (grid2d) {
-                if (lane < 8) {
-                    const int gy = tn.ty0 + lane;
-                    if (gy < prm.grid_h && tn.tx0 < prm.grid_w) {
-                        const size_t n = (size_t)gy * prm.grid_w + tn.tx0;
-                        const int wpx = min(8, prm.grid_w - tn.tx0);
-                        prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + n) * C, (uint32_t)(wpx * C * 4));
-                        if ((n & 3) == 0 && (N & 3) == 0) {
-                            const uint32_t by = (uint32_t)(((wpx * 4) + 15) & ~15);
-                            prefetch_l2_bulk(prm.D + (size_t)tn.b * N + n, by);
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + n, by);
+                                for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + n, by);
+                            }
                         }
                     }
-                }
-            } else if (lane == 0) {
-                prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + tn.n0) * C, (uint32_t)(tn.cnt * C * 4));
-                if ((N & 3) == 0) {
-                    const uint32_t by = (uint32_t)(((tn.cnt * 4) + 15) & ~15);
-                    prefetch_l2_bulk(prm.D + (size_t)tn.b * N + tn.n0, by);
+                } else if (lane == 0) {
+                    prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + tn.n0) * C, (uint32_t)(tn.cnt * C * 4));
+                    if ((N & 3) == 0) {
+                        const uint32_t by = (uint32_t)(((tn.cnt * 4) + 15) & ~15);
+                        prefetch_l2_bulk(prm.D + (size_t)tn.b * N + tn.n0, by);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + tn.n0, by);
+                        for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + tn.n0, by);
+                    }
                 }
             }
+            if (b != geom_b) {
+                geom_b = b;
+                __syncwarp();
+                if (lane < 9) myPose[lane] = prm.R[b * 9 + lane];
+                else if (lane < 12) myPose[lane] = prm.T[b * 3 + lane - 9];
+                else if (lane < 16) myPose[lane] = prm.intr[b * 4 + lane - 12];
+                *reinterpret_cast<float4*>(myW + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KB + 4 * lane));
+                __syncwarp();
+            }
+            const int s = j % NST, sr = j % NREC;
+            const unsigned char* As = base + SM::off_A + s * STAGE_A;
+            // global inputs of this lane's pixel first (their latency hides behind the waits and the dot product)
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f, D0 = 0.f;
+            int n = 0; bool valid = false;
+            if (lane < 16) {
+                if (grid2d) { const int gx = tc.tx0 + (nlr & 7), gy = tc.ty0 + (nlr >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
+                else { valid = nlr < tc.cnt; n = tc.n0 + nlr; }
+                if (valid) {
+                    const float* pp = prm.p + (size_t)b * 3 * N + n;
+                    p0 = __ldg(pp); p1 = __ldg(pp + N); p2 = __ldg(pp + 2 * (size_t)N);
+                    D0 = __ldg(prm.D + (size_t)b * N + n);
+                }
+            }
+            if (gwi == 0) TC6_TRACE(2, j, 0);
+            mbar_wait_parked(&recfree[sr], ((j / NREC) & 1) ^ 1);
+            mbar_wait_parked(&fullB[s], (j / NST) & 1);
+            if (gwi == 0) TC6_TRACE(2, j, 1);
+            float mydot;
+            {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r16) & 7;
+                    const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nlr, c));
+                    const float4 w4 = *reinterpret_cast<const float4*>(myW + blk * 32 + c * 4);
+                    acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
+                }
+                mydot = (acc.x + acc.y) + (acc.z + acc.w);
+                mydot += __shfl_xor_sync(0xffffffffu, mydot, 16);
+            }
+            if (gwi == 0) TC6_TRACE(2, j, 2);
+            if (lane < 16) {                                 // thread per pixel (bundlenet.py:208-224, mask :231)
+                const float* pose = myPose;
+                float mask = 0.f, x = 0.f, y = 0.f, iZ = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, dx = 0.f, dy = 0.f;
+                int x0 = 0, y0 = 0;
+                if (valid) {
+                    const float Dt = D0 + mydot;
+                    rx = pose[0] * p0 + pose[1] * p1 + pose[2] * p2;
+                    ry = pose[3] * p0 + pose[4] * p1 + pose[5] * p2;
+                    rz = pose[6] * p0 + pose[7] * p1 + pose[8] * p2;
+                    const float X = rx * Dt + pose[9], Y = ry * Dt + pose[10], Z = rz * Dt + pose[11];
+                    x = X / Z; y = Y / Z; iZ = 1.0f / Z;
+                    const float u = pose[12] * x + pose[14], v = pose[13] * y + pose[15];
+                    if ((u >= 0.f) && (u <= (float)(w - 1)) && (v >= 0.f) && (v <= (float)(h - 1)) && isfinite(iZ)) {
+                        mask = 1.f;
+                        const float fu = floorf(u), fv = floorf(v);
+                        x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
+                    }
+                }
+                uint32_t o[4], cx[2] = {0u, 0u};
+                if constexpr (FLY) {                             // rows y0-1 .. y0+2 as float offsets, columns x0-1 .. x0+2 as packed pixel indices
+                    o[0] = (uint32_t)(reflect_i(y0 - 1, h) * w * c2); o[1] = (uint32_t)(y0 * w * c2);
+                    o[2] = (uint32_t)(reflect_i(y0 + 1, h) * w * c2); o[3] = (uint32_t)(reflect_i(y0 + 2, h) * w * c2);
+                    cx[0] = (uint32_t)reflect_i(x0 - 1, w) | ((uint32_t)x0 << 16);
+                    cx[1] = (uint32_t)reflect_i(x0 + 1, w) | ((uint32_t)reflect_i(x0 + 2, w) << 16);
+                }
+                if constexpr (!FLY) {
+                    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
+                    o[0] = (uint32_t)((y0 * w + x0) * c2); o[1] = (uint32_t)((y0 * w + x1) * c2);
+                    o[2] = (uint32_t)((y1 * w + x0) * c2); o[3] = (uint32_t)((y1 * w + x1) * c2);
+                }
+                float* rec = sRec + (sr * TILE + nlr) * REC;
+                *reinterpret_cast<uint4*>(rec) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(rec + 4) = make_float4(mask, x, y, iZ);
+                *reinterpret_cast<float4*>(rec + 8) = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
+                *reinterpret_cast<float4*>(rec + 12) = make_float4(dx, dy, __uint_as_float(cx[0]), __uint_as_float(cx[1]));
+            }
+            if (gwi == 0 && lane == 0) sTile[sr * 4] = b;
+            __syncwarp();
+            if (gwi == 0) TC6_TRACE(2, j, 3);
+            if (lane == 0) mbar_arrive(&recs[sr]);
         }
-      }
     } else if (warp < W0 + GW) {
         // ===================================================================== gather warps: records -> taps -> M, q
         setmaxnreg_inc<88>();
@@ -236,7 +287,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         int cur_b = -1, ndump = 0;
 
         auto dump_rb = [&]() {
-            if (ndump > 0) mbar_wait(rbfree, (ndump - 1) & 1);       // helpers consumed the previous hand-over
+            if (ndump > 0) mbar_wait_parked(rbfree, (ndump - 1) & 1);       // the algebra warps consumed the previous hand-over
 #pragma unroll
             for (int u = 0; u < NCH * 4; ++u) rb[u] += __shfl_xor_sync(0xffffffffu, rb[u], 16);
             if (hw == 0) {
@@ -254,7 +305,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         for (int j = 0; j < ntiles; ++j) {
             const int s = j % NREC;
             if (g == 0) TC6_TRACE(0, j, 0);
-            mbar_wait(&recs[s], (j / NREC) & 1);
+            mbar_wait_parked(&recs[s], (j / NREC) & 1);
             if (g == 0) TC6_TRACE(0, j, 1);
             const int b = sTile[s * 4];
             if (b != cur_b) { if (cur_b >= 0) dump_rb(); cur_b = b; }
@@ -276,12 +327,9 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                         tb[5] = ldg4(t00 + C); tb[6] = ldg4(t01 + C); tb[7] = ldg4(t10 + C); tb[8] = ldg4(t11 + C);
                         tb[9] = ldg4(t00 + 2 * C); tb[10] = ldg4(t01 + 2 * C); tb[11] = ldg4(t10 + 2 * C); tb[12] = ldg4(t11 + 2 * C);
                     } else {
-                        const int x0 = (int)o.x, y0 = (int)o.y;
-                        const int X1 = reflect_i(x0 + 1, w), XM = reflect_i(x0 - 1, w), XP = reflect_i(x0 + 2, w);
-                        const int Y1 = reflect_i(y0 + 1, h), YM = reflect_i(y0 - 1, h), YP = reflect_i(y0 + 2, h);
-                        const float* r0 = img + (uint32_t)(y0 * w * c2); const float* r1 = img + (uint32_t)(Y1 * w * c2);
-                        const float* rm = img + (uint32_t)(YM * w * c2); const float* rp = img + (uint32_t)(YP * w * c2);
-                        const uint32_t oM = XM * c2, o0 = x0 * c2, o1 = X1 * c2, oP = XP * c2;
+                        const uint2 cxy = *reinterpret_cast<const uint2*>(rec + pl * REC + 14);
+                        const float* rm = img + o.x; const float* r0 = img + o.y; const float* r1 = img + o.z; const float* rp = img + o.w;
+                        const uint32_t oM = (cxy.x & 0xffffu) * c2, o0 = (cxy.x >> 16) * c2, o1 = (cxy.y & 0xffffu) * c2, oP = (cxy.y >> 16) * c2;
                         tb[1] = ldg4(r0 + oM); tb[2] = ldg4(r0 + o0); tb[3] = ldg4(r0 + o1); tb[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
                         tb[5] = ldg4(r1 + oM); tb[6] = ldg4(r1 + o0); tb[7] = ldg4(r1 + o1); tb[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
                         tb[9] = ldg4(rm + o0); tb[10] = ldg4(rm + o1); tb[11] = ldg4(rp + o0); tb[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
@@ -326,8 +374,8 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 }
                 if (jc == NCH - 1) {
                     m11 = hsum16(m11); m12 = hsum16(m12); m22 = hsum16(m22); q1 = hsum16(q1); q2 = hsum16(q2);
-                    if (hl == 0) {           // totals overwrite the tap offsets / n of this pixel's record (no longer needed)
-                        *reinterpret_cast<float4*>(rec + pl * REC) = make_float4(m11, m12, m22, q1);
+                    if (hl == 0) {           // totals overwrite dx,dy / n of this pixel's record (no longer needed; the tap offsets stay for the prefetcher)
+                        *reinterpret_cast<float4*>(rec + pl * REC + 12) = make_float4(m11, m12, m22, q1);
                         rec[pl * REC + 11] = q2;
                     }
                 }
@@ -337,21 +385,40 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             if (lane == 0) mbar_arrive(&gath[s]);
         }
         if (cur_b >= 0) dump_rb();
-    } else if (warp < W0 + GW + HW) {
-        // ===================================================================== helper warps: geometry, algebra, R rows, drains
-        setmaxnreg_dec<72>();
-        const int hwi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*hwi .. 16*hwi+15, TMEM lanes 32*hwi .. +31
-        const int htid = tid - (W0 + GW) * 32;
+    } else if (warp < W0 + GW + AW) {
+        // ===================================================================== algebra warps: 2x7 algebra, R rows, MMA + TMA issue
+        setmaxnreg_dec<64>();
+        const int awi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*awi .. 16*awi+15
+        const int atid = tid - (W0 + GW) * 32;
+        const int nlr = awi * 16 + r16;
         const SlotLayout L{KB, C};
         unsigned char* Rs = base + SM::off_R;
-        float* myPose = sPose + hwi * 32;
         float cc[28];
 #pragma unroll
         for (int q = 0; q < 28; ++q) cc[q] = 0.f;
-        int gpar = 1, geom_b = -1, spar = 1, scale_b = -1, sspan = -1;
-        TileCoord nxt = tile_coord(prm, t_begin);
-        int nxt_r = (int)((unsigned)t_begin - (unsigned)nxt.b * (unsigned)prm.tiles_per_pair);
+        int scale_b = -1, sspan = -1;
+        float fx = 0.f, fy = 0.f;
+        int rr = (ntiles > 0) ? (int)((unsigned)t_begin % (unsigned)prm.tiles_per_pair) : 0;
+        // issuer state (kept by every lane of warp 0, used by its lane 0)
+        constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, NN);
+        int chain = -1, tic = 0, set = 0, mspan = 0;
+        bool new_span = true;
+        uint32_t accH = 0, accL = 0;
 
+        auto issue_tma = [&](int t) {                        // basis tile t -> stage t % NST (elected thread)
+            const int st = t % NST;
+            const TileCoord tc = tile_coord(prm, t_begin + t);
+            mbar_arrive_expect_tx(&fullB[st], STAGE_A);
+            unsigned char* dst = base + SM::off_A + st * STAGE_A;
+            if (grid2d) {
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[st]);
+            } else {
+                const int row = tc.b * N + tc.n0;
+#pragma unroll
+                for (int blk = 0; blk < 4; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[st]);
+            }
+        };
         auto flush = [&](int sp) {
             float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + sp) * prm.slot_floats;
             // H_cc / g_c / nvalid: 16 pixel-lanes -> warp total (fixed shuffle tree) -> 4 warp partials summed in fixed order
@@ -360,122 +427,43 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 float v = cc[q];
                 v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (lane == 0) sCcs[hwi * 28 + q] = v;
+                if (lane == 0) sCcs[awi * 28 + q] = v;
                 cc[q] = 0.f;
             }
-            mbar_wait(rbdump, sp & 1);                       // the gather warps parked their |diff| sums for this pair
-            helper_bar<HW * 32>();
-            if (htid < C) {
-                float s = 0.f;
+            mbar_wait_parked(rbdump, sp & 1);                // the gather warps parked their |diff| sums for this pair
+            helper_bar<AW * 32>();
+            if (atid < C) {
+                float sum = 0.f;
 #pragma unroll
-                for (int wq = 0; wq < GW; ++wq) s += sRbs[wq * 128 + htid];
-                slot[L.off_rbar() + htid] = s;
+                for (int wq = 0; wq < GW; ++wq) sum += sRbs[wq * 128 + atid];
+                slot[L.off_rbar() + atid] = sum;
             }
-            if (htid < 28) slot[L.off_cc() + htid] = (sCcs[htid] + sCcs[28 + htid]) + (sCcs[56 + htid] + sCcs[84 + htid]);
-            helper_bar<HW * 32>();
+            if (atid < 28) slot[L.off_cc() + atid] = (sCcs[atid] + sCcs[28 + atid]) + (sCcs[56 + atid] + sCcs[84 + atid]);
+            helper_bar<AW * 32>();
             if (lane == 0) mbar_arrive(rbfree);
         };
 
-        // ---- geometry of tile j: records -> sRec[j%3], pair index -> sTile[j%3]
-        auto geom = [&](int j, int tj) {
-            const TileCoord tc = nxt;
-            if (++nxt_r == prm.tiles_per_pair) { nxt_r = 0; ++nxt.b; nxt.tx0 = 0; nxt.ty0 = 0; nxt.n0 = 0; nxt.cnt = grid2d ? TILE : min(TILE, N); }
-            else if (grid2d) { nxt.tx0 += 8; if (nxt.tx0 >= prm.tiles_x * 8) { nxt.tx0 = 0; nxt.ty0 += 8; } }
-            else { nxt.n0 += TILE; nxt.cnt = min(TILE, N - nxt.n0); }
-            const int b = tc.b;
-            if (b != geom_b) {
-                gpar ^= 1; geom_b = b;
-                float* pose = myPose + gpar * 16;
-                __syncwarp();
-                if (lane < 9) pose[lane] = prm.R[b * 9 + lane];
-                else if (lane < 12) pose[lane] = prm.T[b * 3 + lane - 9];
-                else if (lane < 16) pose[lane] = prm.intr[b * 4 + lane - 12];
-                *reinterpret_cast<float4*>(sW + gpar * 128 + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KB + 4 * lane));
-                __syncwarp();
-            }
-            const float* pose = myPose + gpar * 16;
-            const int s = j % 3, sr = j % NREC;
-            const unsigned char* As = base + SM::off_A + s * STAGE_A;
-            if (hwi == 0) TC6_TRACE(1, tj, 0);
-            mbar_wait(&fullB[s], (j / 3) & 1);
-            if (hwi == 0) TC6_TRACE(1, tj, 1);
-            // b.W: lane = (row lane&15, half lane>>4) walks 16 chunks of its row half, rotated so that a quarter-warp hits 8 distinct
-            // 16-B bank groups of the swizzled tile (and of W)
-            float mydot;
-            {
-                const int r = lane & 15, nl = hwi * 16 + r, hf = lane >> 4;
-                const float* wp = sW + gpar * 128;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r) & 7;
-                    const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nl, c));
-                    const float4 w4 = *reinterpret_cast<const float4*>(wp + blk * 32 + c * 4);
-                    acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
-                }
-                mydot = (acc.x + acc.y) + (acc.z + acc.w);
-                mydot += __shfl_xor_sync(0xffffffffu, mydot, 16);
-            }
-            if (hwi == 0) TC6_TRACE(1, tj, 2);
-            if (lane < 16) {                                 // thread per pixel (bundlenet.py:208-224, mask :231)
-                const int nl = hwi * 16 + lane;
-                int n; bool valid;
-                if (grid2d) { const int gx = tc.tx0 + (nl & 7), gy = tc.ty0 + (nl >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
-                else { valid = nl < tc.cnt; n = tc.n0 + nl; }
-                float mask = 0.f, x = 0.f, y = 0.f, iZ = 0.f, rx = 0.f, ry = 0.f, rz = 0.f, dx = 0.f, dy = 0.f;
-                int x0 = 0, y0 = 0;
-                if (valid) {
-                    const float* pp = prm.p + (size_t)b * 3 * N + n;
-                    const float p0 = __ldg(pp), p1 = __ldg(pp + N), p2 = __ldg(pp + 2 * (size_t)N);
-                    const float Dt = __ldg(prm.D + (size_t)b * N + n) + mydot;
-                    rx = pose[0] * p0 + pose[1] * p1 + pose[2] * p2;
-                    ry = pose[3] * p0 + pose[4] * p1 + pose[5] * p2;
-                    rz = pose[6] * p0 + pose[7] * p1 + pose[8] * p2;
-                    const float X = rx * Dt + pose[9], Y = ry * Dt + pose[10], Z = rz * Dt + pose[11];
-                    x = X / Z; y = Y / Z; iZ = 1.0f / Z;
-                    const float u = pose[12] * x + pose[14], v = pose[13] * y + pose[15];
-                    if ((u >= 0.f) && (u <= (float)(w - 1)) && (v >= 0.f) && (v <= (float)(h - 1)) && isfinite(iZ)) {
-                        mask = 1.f;
-                        const float fu = floorf(u), fv = floorf(v);
-                        x0 = (int)fu; y0 = (int)fv; dx = u - fu; dy = v - fv;
-                    }
-                }
-                uint32_t o[4] = {(uint32_t)x0, (uint32_t)y0, 0u, 0u};
-                if constexpr (!FLY) {
-                    const int x1 = min(x0 + 1, w - 1), y1 = min(y0 + 1, h - 1);
-                    o[0] = (uint32_t)((y0 * w + x0) * c2); o[1] = (uint32_t)((y0 * w + x1) * c2);
-                    o[2] = (uint32_t)((y1 * w + x0) * c2); o[3] = (uint32_t)((y1 * w + x1) * c2);
-                }
-                float* rec = sRec + (sr * TILE + nl) * REC;
-                *reinterpret_cast<uint4*>(rec) = make_uint4(o[0], o[1], o[2], o[3]);
-                *reinterpret_cast<float4*>(rec + 4) = make_float4(mask, x, y, iZ);
-                *reinterpret_cast<float4*>(rec + 8) = make_float4(rx, ry, rz, __int_as_float(valid ? n : 0));
-                *reinterpret_cast<float4*>(rec + 12) = make_float4(dx, dy, 0.f, 0.f);
-            }
-            if (hwi == 0 && lane == 0) sTile[sr * 4] = b;
-            __syncwarp();
-            if (hwi == 0) TC6_TRACE(1, tj, 3);
-            if (lane == 0) mbar_arrive(&recs[sr]);
-        };
+        if (awi == 0 && lane == 0)
+            for (int t = 0; t < NST && t < ntiles; ++t) issue_tma(t);      // every stage starts free
 
-        // ---- algebra + R rows of tile j
-        auto s3scale = [&](int j, int b, bool last_of_pair) {
-            const int s = j % 3, sr = j % NREC;
-            if (b != scale_b) { spar ^= 1; scale_b = b; ++sspan; }
-            const float* pose = myPose + spar * 16;
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % NST, sr = j % NREC;
+            const bool last_of_pair = (++rr == prm.tiles_per_pair) || (j == ntiles - 1);
+            if (rr == prm.tiles_per_pair) rr = 0;
             const unsigned char* As = base + SM::off_A + s * STAGE_A;
-            if (hwi == 0) TC6_TRACE(1, j, 4);
-            mbar_wait(&gath[sr], (j / NREC) & 1);
-            if (hwi == 0) TC6_TRACE(1, j, 5);
+            if (awi == 0) TC6_TRACE(1, j, 0);
+            mbar_wait_parked(&gath[sr], (j / NREC) & 1);
+            if (awi == 0) TC6_TRACE(1, j, 1);
+            const int b = sTile[sr * 4];
+            if (b != scale_b) { scale_b = b; ++sspan; fx = __ldg(prm.intr + b * 4); fy = __ldg(prm.intr + b * 4 + 1); }
             float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (lane < 16) {                                 // thread per pixel (bundlenet.py:49-74)
-                const float* rec = sRec + (sr * TILE + hwi * 16 + lane) * REC;
-                const float4 ra = *reinterpret_cast<const float4*>(rec), rbq = *reinterpret_cast<const float4*>(rec + 4),
+                const float* rec = sRec + (sr * TILE + nlr) * REC;
+                const float4 ra = *reinterpret_cast<const float4*>(rec + 12), rbq = *reinterpret_cast<const float4*>(rec + 4),
                              rc = *reinterpret_cast<const float4*>(rec + 8);
                 if (rbq.x != 0.f) {
                     const float m11 = ra.x, m12 = ra.y, m22 = ra.z, q1 = ra.w, q2 = rc.w, x = rbq.y, y = rbq.z, iZ = rbq.w;
                     const float rx = rc.x, ry = rc.y, rz = rc.z;
-                    const float fx = pose[12], fy = pose[13];
                     const float a0[6] = {-fx * (x * y), -fx * (-1.f - x * x), -fx * y, -fx * (-iZ), 0.f, -fx * (x * iZ)};
                     const float a1[6] = {-fy * (1.f + y * y), -fy * (-(x * y)), -fy * (-x), 0.f, -fy * (-iZ), -fy * (y * iZ)};
                     float ux[6], uy[6];
@@ -497,79 +485,99 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     ext[7] = jd0 * u0 + jd1 * u1;
                 }
             }
-            const int r = lane & 15, nl = hwi * 16 + r, hf = lane >> 4;
-            const float sn = __shfl_sync(0xffffffffu, ext[7], r);     // s_n of this lane's row
-            if (hwi == 0) TC6_TRACE(1, j, 6);
-            if (j > 0) mbar_wait(rfree, (j - 1) & 1);
-            if (hwi == 0) TC6_TRACE(1, j, 7);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&recfree[sr]);        // the record buffer may be refilled (everything needed is in registers)
+            const float sn = __shfl_sync(0xffffffffu, ext[7], r16);   // s_n of this lane's row
+            if (awi == 0) TC6_TRACE(1, j, 2);
+            mbar_wait_parked(&fullB[s], (j / NST) & 1);      // long complete; orders the TMA writes before the reads below
+            if (j > 0) {
+                mbar_wait_parked(rfree, (j - 1) & 1);        // MMAs of tile j-1 done: R / A_lo / R_lo and stage (j-1) % NST are free
+                if (awi == 0 && lane == 0 && j - 1 + NST < ntiles) issue_tma(j - 1 + NST);
+            }
+            if (awi == 0) TC6_TRACE(1, j, 3);
             if (lane < 16) {                                 // R columns 128..134 = [v(6) | t], column 135 stays zero
                 const float4 e0 = make_float4(tf32_rna(ext[0]), tf32_rna(ext[1]), tf32_rna(ext[2]), tf32_rna(ext[3]));
                 const float4 e1 = make_float4(tf32_rna(ext[4]), tf32_rna(ext[5]), tf32_rna(ext[6]), 0.f);
-                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 0)) = e0;
-                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nl, 1)) = e1;
+                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nlr, 0)) = e0;
+                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nlr, 1)) = e1;
                 if constexpr (MODE == 3) {
-                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nl, 0)) = make_float4(ext[0] - e0.x, ext[1] - e0.y, ext[2] - e0.z, ext[3] - e0.w);
-                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nl, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nlr, 0)) = make_float4(ext[0] - e0.x, ext[1] - e0.y, ext[2] - e0.z, ext[3] - e0.w);
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nlr, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
                 }
             }
-            // R rows: lane = (row lane&15, half lane>>4) walks the 16 chunks of its half row (rotated: conflict-free quarter-warps)
+            // R rows (and the split parts): elementwise on the lane's half row, so walk the PHYSICAL 16-B slots (rotated by the row: every
+            // quarter-warp touches 8 distinct bank groups) and skip the swizzle arithmetic
+            const uint32_t rowoff = hf * 16384 + nlr * 128;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-                const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r) & 7;
-                const uint32_t off = blk * 8192 + sw128_32b_off(nl, c);
+                const uint32_t off = rowoff + (i >> 3) * 8192 + (((i & 7) + r16) & 7) * 16;
                 const float4 bv = *reinterpret_cast<const float4*>(As + off);
                 const float4 pv = make_float4(sn * bv.x, sn * bv.y, sn * bv.z, sn * bv.w);
-                const float4 hv = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
+                float4 hv;
+                if constexpr (MODE == 3) hv = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
+                else hv = make_float4(tf32_rna_bits(pv.x), tf32_rna_bits(pv.y), tf32_rna_bits(pv.z), tf32_rna_bits(pv.w));   // MMA drops the low 13 bits
                 *reinterpret_cast<float4*>(Rs + off) = hv;
                 if constexpr (MODE >= 2)
                     *reinterpret_cast<float4*>(base + SM::off_Alo + off) = make_float4(bv.x - tf32_trunc(bv.x), bv.y - tf32_trunc(bv.y), bv.z - tf32_trunc(bv.z), bv.w - tf32_trunc(bv.w));
                 if constexpr (MODE == 3)
                     *reinterpret_cast<float4*>(base + SM::off_Rlo + off) = make_float4(pv.x - hv.x, pv.y - hv.y, pv.z - hv.z, pv.w - hv.w);
             }
-            if (hwi == 0) TC6_TRACE(1, j, 8);
             fence_proxy_async_smem();
-            __syncwarp();
-            if (hwi == 0) TC6_TRACE(1, j, 9);
-            if (lane == 0) mbar_arrive(ready);
+            if (awi == 0) TC6_TRACE(1, j, 4);
+            helper_bar<AW * 32>();                           // all 64 rows written
+            if (awi == 0) {
+                if (lane == 0) {                             // ---- tcgen05.mma issue for this tile
+                    if (new_span) { mbar_wait_parked(tmemfree, (mspan & 1) ^ 1); accL = 0; new_span = false; }
+                    if (tic == 0) { ++chain; set = chain & 1; mbar_wait_parked(&drained[set], ((chain >> 1) & 1) ^ 1); accH = 0; }
+                    tc_fence_after_sync();
+                    const uint32_t ahi = smem_u32(base + SM::off_A + s * STAGE_A);
+                    const uint32_t rhi = smem_u32(base + SM::off_R), rlo = smem_u32(base + SM::off_Rlo), alo = smem_u32(base + SM::off_Alo);
+#pragma unroll
+                    for (int pass = 0; pass < MODE; ++pass) {
+                        const uint32_t a0 = (pass == 1) ? alo : ahi;
+                        const uint32_t r0 = (pass == 2) ? rlo : rhi;
+                        const uint32_t dcol = tmem + (pass == 0 ? set * NN : ACCL);
+#pragma unroll
+                        for (int kk = 0; kk < TILE / 8; ++kk) {
+                            mma_tf32_ss(dcol, make_desc_mn_sw128_32b(a0 + kk * 1024, 8192, 512),
+                                        make_desc_mn_sw128_32b(r0 + kk * 1024, 8192, 512), idesc, pass == 0 ? accH : accL);
+                            if (pass == 0) accH = 1; else accL = 1;
+                        }
+                    }
+                    mma_commit(rfree);
+                    if (++tic == CHAIN) { mma_commit(&chain_done[set]); tic = 0; }
+                    if (last_of_pair) { if (tic > 0) mma_commit(&chain_done[set]); mma_commit(flushb); ++mspan; tic = 0; new_span = true; }
+                }
+                __syncwarp();
+            }
+            if (awi == 0) TC6_TRACE(1, j, 5);
             if (last_of_pair) flush(sspan);
-        };
-
-        if (ntiles > 0) geom(0, -1);
-        int b_cur = (ntiles > 0) ? tile_coord(prm, t_begin).b : -1;
-        for (int j = 0; j < ntiles; ++j) {
-            int b_next = -1;
-            if (j + 1 < ntiles) { b_next = nxt.b; geom(j + 1, j); }
-            s3scale(j, b_cur, b_next != b_cur);
-            b_cur = b_next;
         }
     } else {
         // ===================================================================== drainer warps: TMEM -> partial slots, fully asynchronous
-        setmaxnreg_dec<56>();
-        const int dq = warp - (W0 + GW + HW);                // TMEM lane quadrant (= warp % 4)
+        setmaxnreg_dec<40>();
+        const int dq = warp - (W0 + GW + AW);                // TMEM lane quadrant (= warp % 4)
         const SlotLayout L{KB, C};
         auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
             const int row = dq * 32 + lane;
             const uint32_t tq = tmem + ((uint32_t)(dq * 32) << 16) + col0;
-            float v[32];
+            float v[16];
 #pragma unroll 1
-            for (int cb = 0; cb < 4; ++cb) {
-                tmem_ld_32x32(tq + cb * 32, v);
-                float* dst = slot + (size_t)(cb * 32) * KB + row;
+            for (int cb = 0; cb < 8; ++cb) {
+                tmem_ld_32x16(tq + cb * 16, v);
+                float* dst = slot + (size_t)(cb * 16) * KB + row;
                 if (overwrite) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) dst[(size_t)j * KB] = v[j];
+                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KB] = v[j];
                 } else {
+                    float o[16];
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        float o[16];
+                    for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)j * KB];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)(16 * hh + j) * KB];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) dst[(size_t)(16 * hh + j) * KB] = o[j] + v[16 * hh + j];
-                    }
+                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KB] = o[j] + v[j];
                 }
             }
-            tmem_ld_32x32(tq + 128, v);
+            tmem_ld_32x16(tq + 128, v);
             float* dst = slot + L.off_ext() + row;
 #pragma unroll
             for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KB] = v[r]; else dst[r * KB] += v[r]; }
@@ -581,7 +589,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         auto drain_hi = [&]() {
             const int set = chain & 1;
             float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats;
-            mbar_wait_sleep(&chain_done[set], (chain >> 1) & 1);
+            mbar_wait_parked(&chain_done[set], (chain >> 1) & 1);
             tc_fence_after_sync();
             drain_region(slot, set * NN, first);
             first = false;
@@ -593,7 +601,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             if (tic > 0) drain_hi();
             if constexpr (MODE >= 2) {
                 float* slot = prm.partials + ((size_t)blockIdx.x * prm.max_span + span) * prm.slot_floats;
-                mbar_wait_sleep(flushb, span & 1);
+                mbar_wait_parked(flushb, span & 1);
                 tc_fence_after_sync();
                 drain_region(slot, ACCL, false);
                 tc_fence_before_sync();
@@ -620,7 +628,7 @@ template <int NCH, bool FLY, int MODE>
 static int launch6(const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
 {
     auto kern = lm_build_tc6_kernel<NCH, FLY, MODE>;
-    const int smem = Smem<MODE>::bytes;
+    const int smem = Smem<MODE, FLY>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("lm_build_tc6: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return BANET_ERR_CUDA; }
     kern<<<grid, THREADS, smem, st>>>(tm, prm);

@@ -34,6 +34,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
 
+// wait with a hardware suspend-time hint: the warp is parked by the barrier unit (no issue slots burnt on polling) and woken on completion
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity), "r"(0x989680) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {      // for single-thread role warps: back off
     while (!mbar_try_wait(bar, parity)) { __nanosleep(40); }
 }
@@ -67,6 +72,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, int
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {      // bytes % 16 == 0, p 16-B aligned
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2_line(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void prefetch_l2_tensor_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
                  :: "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -108,6 +114,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* out) {
     for (int i = 0; i < 32; ++i) out[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float* out) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) out[i] = __uint_as_float(r[i]);
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for an MN-major 32-bit (tf32) operand.  The only canonical layout the
 // tensor core accepts for MN-major tf32 is SWIZZLE_128B with 32-byte atomicity (LayoutType 1,
@@ -137,6 +155,8 @@ __device__ __forceinline__ float tf32_rna(float x) {          // round to neares
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
 }
+// round-to-nearest (ties away) for an operand whose low 13 bits the tensor core ignores anyway: one integer add, no mask
+__device__ __forceinline__ float tf32_rna_bits(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 }}  // namespace banet::tc
