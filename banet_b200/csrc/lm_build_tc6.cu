@@ -227,7 +227,12 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nlr, c));
                     const float4 w4 = *reinterpret_cast<const float4*>(myW + blk * 32 + c * 4);
                     acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
+                    if constexpr (MODE == 1)     // single-pass mode: round the basis tile to tf32 IN PLACE (nearest, unbiased) — the tensor core
+                                                 // would truncate it (biased: relH 1e-5 instead of <1e-6); D~ above still uses the exact values
+                        *reinterpret_cast<float4*>(const_cast<unsigned char*>(As) + blk * 8192 + sw128_32b_off(nlr, c)) =
+                            make_float4(tf32_rna_mask(bv.x), tf32_rna_mask(bv.y), tf32_rna_mask(bv.z), tf32_rna_mask(bv.w));
                 }
+                if constexpr (MODE == 1) fence_proxy_async_smem();      // the MMA reads this stage through the async proxy
                 mydot = (acc.x + acc.y) + (acc.z + acc.w);
                 mydot += __shfl_xor_sync(0xffffffffu, mydot, 16);
             }

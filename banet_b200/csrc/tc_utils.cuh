@@ -157,6 +157,7 @@ __device__ __forceinline__ float tf32_rna(float x) {          // round to neares
 }
 // round-to-nearest (ties away) for an operand whose low 13 bits the tensor core ignores anyway: one integer add, no mask
 __device__ __forceinline__ float tf32_rna_bits(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
+__device__ __forceinline__ float tf32_rna_mask(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_trunc(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 }}  // namespace banet::tc

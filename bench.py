@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
+                    help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
+    ap.add_argument("--no-precision-check", action="store_true")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x1", "tf32x2", "tf32x3"],
                     help="contraction path of the build kernel: auto = tensor cores (tcgen05 tf32 split-A) when K=128, else fp32 SIMT")
     return ap.parse_args()
@@ -189,6 +192,9 @@ def main():
     C, K, nb, iters = args.channels, args.bases, args.nb, args.iters
     sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 2 + 1000 * rank,
                           device=dev, dtype=torch.float32)
+    if args.layout == "f2":            # keep only the feature third of conv2 (the gradients are recomputed on the fly by the kernel)
+        for l in sc.levels:
+            l.conv2 = l.conv2[..., :C].contiguous()
     levels = [ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid) for l in sc.levels]
     PREC = {"auto": _lib.PREC_AUTO, "fp32": _lib.PREC_FP32_SIMT, "tf32x1": _lib.PREC_TF32X1, "tf32x2": _lib.PREC_TF32X2,
             "tf32x3": _lib.PREC_TF32X3}[args.precision]
@@ -217,6 +223,19 @@ def main():
         out, status = step()
     barrier()
     assert int(status.abs().max()) == 0, "solver reported a non-SPD / non-finite system"
+
+    # ---- accuracy of the timed precision mode on THIS workload: outputs against the FP32 SIMT path (pinned to the oracle by tests/) ----
+    precision_check = None
+    if rank == 0 and not args.no_precision_check and PREC != _lib.PREC_FP32_SIMT:
+        rf = lambda a, b: float(((a - b).norm() / b.norm()).item())
+        R1, T1, W1, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, precision=PREC)
+        R0_, T0_, W0_, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0,
+                                     precision=_lib.PREC_FP32_SIMT)
+        errs = {"R": rf(R1, R0_), "T": rf(T1, T0_), "W": rf(W1, W0_)}
+        precision_check = {"vs": "fp32_simt path, same inputs, all levels x iterations", "rel_fro": errs, "tolerance": 1e-4,
+                           "ok": max(errs.values()) < 1e-4}
+        del R1, T1, W1, R0_, T0_, W0_
+    barrier()
 
     sampler = ClockSampler(local); sampler.start()
     ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
@@ -259,7 +278,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else "lm_build_tc_kernel"
+    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else "lm_build_tc6_kernel"
     roofline = {"bound": "hbm", "kernel": f"{kname} (+lm_reduce_kernel) @640x480", "achieved": top["gbs"], "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": top["gbs"] / peak, "frac_3c_layout": top["gbs_3c_layout"] / peak,
                 "traffic": traffic, "per_level": per_level,
@@ -287,10 +306,11 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_pairs": world * nb, "lm_iterations_per_step": total_iters,
                            "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": args.precision,
-                           "conv2_layout": "[F2|gx|gy] (3C channels, the reference's BundleIteration boundary)",
+                           "conv2_layout": "[F2|gx|gy] (3C channels, the reference's BundleIteration boundary)" if args.layout == "concat"
+                                           else "F2 only (C channels); the kernel recomputes gx, gy on the fly (reference grad_fixed, bundlenet.py:92-100)",
                            "l2": "inputs (~33 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "parallelism": f"pairs sharded over {world} GPU(s), one all-gather of (R,T,W) per step"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 5),
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 5), "precision_check": precision_check,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:

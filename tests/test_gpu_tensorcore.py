@@ -132,3 +132,27 @@ def test_lm_run_tensorcore_vs_oracle_outputs():
         if prec in (0, 3):
             for e, f in zip(errs, floor):
                 assert e < max(1e-4, 2.0 * f)
+
+
+@pytest.mark.parametrize("fly,grid", [(False, True), (True, True), (False, False)])
+@pytest.mark.parametrize("prec", [1, 2, 3])
+def test_lm_build_tensorcore_long_tile_runs(prec, fly, grid):
+    """Many tiles per CTA (ring wrap of the TMA stages and record buffers, several TMEM chains and two pair spans per CTA):
+    240x320, 2 pairs = 2400 tiles over 148 CTAs.  Checked against the FP32 SIMT path (itself pinned to the oracle above),
+    plus run-to-run bit reproducibility."""
+    from banet_b200 import ops, synth
+    sc = synth.make_scene(nb=2, H=240, W=320, C=128, K=128, level_ids=(3,), seed=17, device="cuda", dtype=torch.float32)
+    lv = sc.levels[0]
+    conv2 = lv.conv2[..., :128].contiguous() if fly else lv.conv2
+    L = ops.Level(lv.conv1, conv2, lv.intr, lv.p, lv.D, lv.B, grid=lv.grid if grid else None)
+    Wt = sc.W0 + 0.01 * torch.randn(sc.W0.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    Hs, gs, rbs, nvs = ops.lm_build(L, sc.R0, sc.T0, Wt, precision=0)
+    H, g, rbar, nv = ops.lm_build(L, sc.R0, sc.T0, Wt, precision=prec)
+    H2, g2, rbar2, nv2 = ops.lm_build(L, sc.R0, sc.T0, Wt, precision=prec)
+    assert torch.equal(H, H2) and torch.equal(g, g2) and torch.equal(rbar, rbar2)
+    assert torch.equal(nv, nvs)
+    tol = {1: 5e-4, 2: 1e-4, 3: 2e-6}[prec]
+    eH, eg = rel_fro(H, Hs), rel_fro(g, gs)
+    print(f"prec={prec} fly={fly} grid={grid}: relH={eH:.2e} relg={eg:.2e}")
+    assert eH < tol and eg < tol
+    assert rel_fro(H[:, :6, :6], Hs[:, :6, :6]) < 2e-5 and rel_fro(rbar, rbs) < 2e-5
