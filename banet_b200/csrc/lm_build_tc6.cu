@@ -156,6 +156,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         float* myPose = sPose + gwi * 16;
         float* myW = sW + gwi * 128;
         int geom_b = -1;
+        uint32_t dseed = 0;                                  // MODE 1: dither seed of the current pair
         TileCoord nxt = tile_coord(prm, t_begin);
         int nxt_r = (int)((unsigned)t_begin - (unsigned)nxt.b * (unsigned)prm.tiles_per_pair);
         for (int j = 0; j < ntiles; ++j) {
@@ -198,6 +199,9 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 else if (lane < 12) myPose[lane] = prm.T[b * 3 + lane - 9];
                 else if (lane < 16) myPose[lane] = prm.intr[b * 4 + lane - 12];
                 *reinterpret_cast<float4*>(myW + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KB + 4 * lane));
+                if constexpr (MODE == 1)     // a pure function of the inputs that changes whenever the iterate changes (see the rounding below)
+                    dseed = (__float_as_uint(__ldg(prm.W + (size_t)b * KB)) * 0x9E3779B1u) ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KB + 1)) * 0x85EBCA77u)
+                          ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KB + 2)) * 0xC2B2AE3Du) ^ __float_as_uint(__ldg(prm.T + b * 3)) ^ (uint32_t)b;
                 __syncwarp();
             }
             const int s = j % NST, sr = j % NREC;
@@ -205,14 +209,12 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             // global inputs of this lane's pixel first (their latency hides behind the waits and the dot product)
             float p0 = 0.f, p1 = 0.f, p2 = 0.f, D0 = 0.f;
             int n = 0; bool valid = false;
-            if (lane < 16) {
-                if (grid2d) { const int gx = tc.tx0 + (nlr & 7), gy = tc.ty0 + (nlr >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
-                else { valid = nlr < tc.cnt; n = tc.n0 + nlr; }
-                if (valid) {
-                    const float* pp = prm.p + (size_t)b * 3 * N + n;
-                    p0 = __ldg(pp); p1 = __ldg(pp + N); p2 = __ldg(pp + 2 * (size_t)N);
-                    D0 = __ldg(prm.D + (size_t)b * N + n);
-                }
+            if (grid2d) { const int gx = tc.tx0 + (nlr & 7), gy = tc.ty0 + (nlr >> 3); valid = gx < prm.grid_w && gy < prm.grid_h; n = gy * prm.grid_w + gx; }
+            else { valid = nlr < tc.cnt; n = tc.n0 + nlr; }
+            if (lane < 16 && valid) {
+                const float* pp = prm.p + (size_t)b * 3 * N + n;
+                p0 = __ldg(pp); p1 = __ldg(pp + N); p2 = __ldg(pp + 2 * (size_t)N);
+                D0 = __ldg(prm.D + (size_t)b * N + n);
             }
             if (gwi == 0) TC6_TRACE(2, j, 0);
             mbar_wait_parked(&recfree[sr], ((j / NREC) & 1) ^ 1);
@@ -227,10 +229,21 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nlr, c));
                     const float4 w4 = *reinterpret_cast<const float4*>(myW + blk * 32 + c * 4);
                     acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
-                    if constexpr (MODE == 1)     // single-pass mode: round the basis tile to tf32 IN PLACE (nearest, unbiased) — the tensor core
-                                                 // would truncate it (biased: relH 1e-5 instead of <1e-6); D~ above still uses the exact values
+                    if constexpr (MODE == 1) {
+                        // single-pass mode: round the basis tile to tf32 IN PLACE.  The tensor core would truncate it (biased: relH 1e-5);
+                        // round-to-nearest is unbiased per launch (relH < 1e-6) but is the SAME perturbation of the basis at every LM
+                        // iteration, so its effect adds up coherently over a solve (W off by 1e-3 after 20 iterations).  Stochastic rounding
+                        // with a dither hashed from (iterate, pixel, column) is unbiased AND changes with the iterate, like the rounding
+                        // of R does; it is a pure function of the inputs, so results stay bit-reproducible.
+                        uint32_t hsh = dseed ^ ((uint32_t)n * 0x9E3779B1u) ^ ((uint32_t)(blk * 8 + c) * 0x85EBCA77u);
+                        hsh ^= hsh >> 16; hsh *= 0x7FEB352Du; hsh ^= hsh >> 15;
+                        uint32_t hs2 = hsh * 0x846CA68Bu; hs2 ^= hs2 >> 16;
                         *reinterpret_cast<float4*>(const_cast<unsigned char*>(As) + blk * 8192 + sw128_32b_off(nlr, c)) =
-                            make_float4(tf32_rna_mask(bv.x), tf32_rna_mask(bv.y), tf32_rna_mask(bv.z), tf32_rna_mask(bv.w));
+                            make_float4(__uint_as_float((__float_as_uint(bv.x) + (hsh & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.y) + ((hsh >> 13) & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.z) + (hs2 & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.w) + ((hs2 >> 13) & 0x1fffu)) & 0xFFFFE000u));
+                    }
                 }
                 if constexpr (MODE == 1) fence_proxy_async_smem();      // the MMA reads this stage through the async proxy
                 mydot = (acc.x + acc.y) + (acc.z + acc.w);

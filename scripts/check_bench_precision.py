@@ -18,9 +18,11 @@ def run(prec, fly):
     return ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, precision=prec)
 R0, T0, W0, st = run(_lib.PREC_FP32_SIMT, False)
 print(f"fp32 simt: status {int(st.abs().max())}; moved R by {rf(R0, sc.R0):.2e}, T by {rf(T0, sc.T0):.2e}, |W| {W0.norm().item():.3e}")
-for name, prec in (("tf32x3", 3), ("tf32x2", 2), ("tf32x1", 1)):
-    for fly in (False, True):
+modes = [m for m in (("tf32x3", 3), ("tf32x2", 2), ("tf32x1", 1)) if str(m[1]) in os.environ.get("BANET_PRECS", "1,2,3").split(",")]
+for name, prec in modes:
+    for fly in (False,):
         R, T, W, st = run(prec, fly)
         print(f"{name} fly={int(fly)}: rel-fro vs fp32 simt  R {rf(R, R0):.2e}  T {rf(T, T0):.2e}  W {rf(W, W0):.2e}  status {int(st.abs().max())}")
+        if not fly: print("    per pair W:", " ".join(f"{rf(W[i], W0[i]):.1e}" for i in range(nb)))
 R, T, W, st = run(_lib.PREC_FP32_SIMT, True)
 print(f"fp32 simt fly=1: R {rf(R, R0):.2e}  T {rf(T, T0):.2e}  W {rf(W, W0):.2e}")
