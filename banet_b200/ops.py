@@ -105,10 +105,14 @@ def compute_coordinates(points: Tensor, intr: Tensor, normalize: bool = True) ->
     return p
 
 
-def grad_fixed_concat(F: Tensor, swap_halves: bool = False) -> Tensor:
+def grad_fixed_concat(F: Tensor, swap_halves: bool = False, out: Optional[Tensor] = None) -> Tensor:
+    """[nb,h,w,C] -> [nb,h,w,3C] = [F | gradx | grady] (reference bundlenet.py:92-100 + the concat of :386-389); `out` reuses a buffer."""
     lib = load()
     f = _chk(F, "F"); nb, h, w, Cc = f.shape
-    out = torch.empty(nb, h, w, 3 * Cc, device=f.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(nb, h, w, 3 * Cc, device=f.device, dtype=torch.float32)
+    else:
+        out = _chk(out, "out", (nb, h, w, 3 * Cc))
     check(lib.banet_grad_fixed_concat(f.data_ptr(), nb, h, w, Cc, int(swap_halves), out.data_ptr(), _stream()),
           "banet_grad_fixed_concat")
     return out

@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
+    ap.add_argument("--e2e-boundary", default="features", choices=["features", "concat"],
+                    help="host buffers of the e2e leg: 'features' = the layer boundary of the reference's BundleResize (bundlenet.py:376-399): "
+                         "feature maps in, [F2|gx|gy] derived on the device each step (banet_grad_fixed_concat); 'concat' = the 3C tensor itself")
     ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x1", "tf32x2", "tf32x3"],
                     help="contraction path of the build kernel: auto = tensor cores (tcgen05 tf32 split-A) when K=128, else fp32 SIMT")
     return ap.parse_args()
@@ -326,10 +329,16 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
     from banet_b200 import dist as bdist
     host = []
     h2d = 0
+    C = args.channels
+    feat = args.e2e_boundary == "features" and args.layout == "concat"
+    stage = []                                   # device staging of the feature third of conv2 (features boundary)
     for l in sc.levels:
         tens = {}
         for name in ("conv1", "conv2", "intr", "p", "D", "B"):
             t = getattr(l, name)
+            if name == "conv2" and feat:
+                t = t[..., :C].contiguous()
+                stage.append(torch.empty_like(t))
             ht = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
             ht.copy_(t)
             tens[name] = ht; h2d += ht.numel() * 4
@@ -341,9 +350,13 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
 
     def e2e_step():
         lvls = []
-        for l, tens in zip(sc.levels, host):
+        for li, (l, tens) in enumerate(zip(sc.levels, host)):
             for name, ht in tens.items():
-                getattr(l, name).copy_(ht, non_blocking=True)           # host -> device, every step
+                if name == "conv2" and feat:                            # features in, [F2|gx|gy] rebuilt on the device (bundlenet.py:386-389)
+                    stage[li].copy_(ht, non_blocking=True)
+                    ops.grad_fixed_concat(stage[li], out=l.conv2)
+                else:
+                    getattr(l, name).copy_(ht, non_blocking=True)       # host -> device, every step
             lvls.append(ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid))
         R0 = hR.to(dev, non_blocking=True); T0 = hT.to(dev, non_blocking=True); W0 = hW.to(dev, non_blocking=True)
         R, T, W, status = ops.lm_run(lvls, args.iters, R0, T0, W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws,
@@ -372,6 +385,9 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
     per = ms / args.e2e_steps * 1e-3
     return {"value": world * args.nb * total_iters / per, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
             "d2h_bytes_per_step": d2h, "ms_per_step": per * 1e3, "steps": args.e2e_steps,
+            "boundary": ("feature maps (C channels) + conv1, p, D, B, intr in pinned host memory; [F2|gx|gy] derived on the device every step "
+                         "(banet_grad_fixed_concat), as the reference's BundleResize does (bundlenet.py:386-389)") if feat else
+                        "every level tensor, conv2 as the 3C [F2|gx|gy] tensor, in pinned host memory",
             "note": "pinned host -> device copy of every level tensor + solve + device -> host of (R,T,W) per step"}
 
 
