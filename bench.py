@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="pair chunks of the host pipeline (copy of chunk k+1 overlaps the solve of chunk k)")
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
@@ -325,46 +326,35 @@ def main():
 
 
 def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
-    from banet_b200 import ops
+    """The call a user with host-resident inputs makes: banet_b200.host_pipeline.HostSolver (pair chunks, H2D of chunk k+1
+    overlapping the solve of chunk k); every step copies every level tensor host->device and the result device->host."""
     from banet_b200 import dist as bdist
-    host = []
-    h2d = 0
+    from banet_b200.host_pipeline import HostSolver
     C = args.channels
     feat = args.e2e_boundary == "features" and args.layout == "concat"
-    stage = []                                   # device staging of the feature third of conv2 (features boundary)
+    host = []
     for l in sc.levels:
-        tens = {}
+        tens = {"grid": l.grid}
         for name in ("conv1", "conv2", "intr", "p", "D", "B"):
             t = getattr(l, name)
             if name == "conv2" and feat:
                 t = t[..., :C].contiguous()
-                stage.append(torch.empty_like(t))
             ht = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
             ht.copy_(t)
-            tens[name] = ht; h2d += ht.numel() * 4
+            tens[name] = ht
         host.append(tens)
+    solver = HostSolver(host, derive_gradients=feat, chunks=args.e2e_chunks, device=dev, precision=prec)
     hR = sc.R0.cpu().pin_memory(); hT = sc.T0.cpu().pin_memory(); hW = sc.W0.cpu().pin_memory()
-    h2d += (hR.numel() + hT.numel() + hW.numel()) * 4
+    h2d = solver.h2d_bytes + (hR.numel() + hT.numel() + hW.numel()) * 4
     oR = torch.empty_like(hR).pin_memory(); oT = torch.empty_like(hT).pin_memory(); oW = torch.empty_like(hW).pin_memory()
     d2h = (oR.numel() + oT.numel() + oW.numel()) * 4 * world
 
     def e2e_step():
-        lvls = []
-        for li, (l, tens) in enumerate(zip(sc.levels, host)):
-            for name, ht in tens.items():
-                if name == "conv2" and feat:                            # features in, [F2|gx|gy] rebuilt on the device (bundlenet.py:386-389)
-                    stage[li].copy_(ht, non_blocking=True)
-                    ops.grad_fixed_concat(stage[li], out=l.conv2)
-                else:
-                    getattr(l, name).copy_(ht, non_blocking=True)       # host -> device, every step
-            lvls.append(ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid))
-        R0 = hR.to(dev, non_blocking=True); T0 = hT.to(dev, non_blocking=True); W0 = hW.to(dev, non_blocking=True)
-        R, T, W, status = ops.lm_run(lvls, args.iters, R0, T0, W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws,
-                                     precision=prec)
+        R, T, W, status = solver.solve(hR, hT, hW, args.iters, mlp_packed=packed, l2_regularizer_base=1000.0,
+                                       out=None if world > 1 else (oR, oT, oW))
         if world > 1:
             R, T, W = bdist.all_gather_solution(R, T, W)
             return R.cpu(), T.cpu(), W.cpu()
-        oR.copy_(R, non_blocking=True); oT.copy_(T, non_blocking=True); oW.copy_(W, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return oR, oT, oW
 
@@ -388,7 +378,9 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
             "boundary": ("feature maps (C channels) + conv1, p, D, B, intr in pinned host memory; [F2|gx|gy] derived on the device every step "
                          "(banet_grad_fixed_concat), as the reference's BundleResize does (bundlenet.py:386-389)") if feat else
                         "every level tensor, conv2 as the 3C [F2|gx|gy] tensor, in pinned host memory",
-            "note": "pinned host -> device copy of every level tensor + solve + device -> host of (R,T,W) per step"}
+            "api": f"banet_b200.host_pipeline.HostSolver(chunks={args.e2e_chunks}).solve",
+            "note": "pinned host -> device copy of every level tensor + solve + device -> host of (R,T,W) per step; copies of pair-chunk k+1 "
+                    "overlap the solve of chunk k"}
 
 
 if __name__ == "__main__":
