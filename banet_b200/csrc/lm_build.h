@@ -12,8 +12,8 @@ struct BuildParams {
     long long total_tiles;
     int grid_w, grid_h, tiles_x;      // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
     int hdd_transposed;
-    int pf_taps;                      // tuning: per-lane L2 prefetch of the next tile's tap lines (on by default)
-    int pf_conv2;                     // tuning: predicted conv2-footprint L2 prefetch (off by default)
+    int pf_taps;                      // tuning (generation 5 only, BANET_TC_PF_TAPS=1): per-lane L2 prefetch of the next tile's tap lines; off: not a win
+    int pf_conv2;                     // tuning (generation 5 only, BANET_TC_PF_CONV2=1): predicted conv2-footprint L2 prefetch; off: not a win
     long long* trace;                 // optional debug timeline buffer (NULL in production)               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
 };
 

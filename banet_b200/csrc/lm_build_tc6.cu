@@ -60,14 +60,14 @@ template <int MODE, bool FLY> struct Smem {
 };
 
 __device__ __forceinline__ long long gtime6() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// debug timeline (BANET_TC_TRACE_PTR): CTA 1, gather warp 0 (role 0) and helper warp 0 (role 1), tiles 16..47, 12 stamps each
+// debug timeline (BANET_TC_TRACE_PTR): CTA 1, gather warp 0 (role 0), algebra warp 0 (role 1) and geometry warp 0 (role 2), tiles 16..47, 12 stamps each
 #ifdef BANET_TC6_TRACE_ON
 #define TC6_TRACE(role, it, slot) do { if (prm.trace && blockIdx.x == 1 && lane == 0 && (it) >= 16 && (it) < 48) \
         prm.trace[(((role) * 32 + ((it) - 16)) * 12) + (slot)] = gtime6(); } while (0)
 #else
 #define TC6_TRACE(role, it, slot) do { } while (0)
 #endif
-template <int NT> __device__ __forceinline__ void helper_bar() { asm volatile("bar.sync 2, %0;" :: "n"(NT) : "memory"); }
+template <int NT> __device__ __forceinline__ void team_bar() { asm volatile("bar.sync 2, %0;" :: "n"(NT) : "memory"); }
 __device__ __forceinline__ int reflect_i(int i, int n) { i = i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); return i < 0 ? 0 : i; }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float hsum16(float v) {
@@ -449,7 +449,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 cc[q] = 0.f;
             }
             mbar_wait_parked(rbdump, sp & 1);                // the gather warps parked their |diff| sums for this pair
-            helper_bar<AW * 32>();
+            team_bar<AW * 32>();
             if (atid < C) {
                 float sum = 0.f;
 #pragma unroll
@@ -457,7 +457,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 slot[L.off_rbar() + atid] = sum;
             }
             if (atid < 28) slot[L.off_cc() + atid] = (sCcs[atid] + sCcs[28 + atid]) + (sCcs[56 + atid] + sCcs[84 + atid]);
-            helper_bar<AW * 32>();
+            team_bar<AW * 32>();
             if (lane == 0) mbar_arrive(rbfree);
         };
 
@@ -542,7 +542,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             }
             fence_proxy_async_smem();
             if (awi == 0) TC6_TRACE(1, j, 4);
-            helper_bar<AW * 32>();                           // all 64 rows written
+            team_bar<AW * 32>();                           // all 64 rows written
             if (awi == 0) {
                 if (lane == 0) {                             // ---- tcgen05.mma issue for this tile
                     if (new_span) { mbar_wait_parked(tmemfree, (mspan & 1) ^ 1); accL = 0; new_span = false; }
