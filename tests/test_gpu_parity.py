@@ -278,3 +278,23 @@ def test_full_size_properties():
     assert status.item() == 0
     e0 = (sc.T0 - sc.T_true).norm().item(); e1 = (T - sc.T_true).norm().item()
     assert e1 < 0.05 * e0 and (W - sc.W_true).norm().item() < 0.2 * sc.W_true.norm().item()
+
+
+def test_cfg1_reference_cpu_case():
+    """BASELINE.json configs[0] — the reference's own CPU-runnable case: one 2-frame pair, 160x120 single scale, K=16 depth
+    bases, 3 LM iterations with the lambda-MLP (C=32 to keep the float64 oracle's materialised J quick) — whole solve against
+    the oracle at the north-star tolerance, through banet_lm_run and through the mirror class."""
+    ops = _ops()
+    sc = scene_case(nb=1, H=120, W=160, C=32, K=16, level_ids=(3,), seed=1235, dtype=torch.float32)
+    lv = sc.levels[0]
+    mlp = mlp_for(32, 3)
+    a = oracle_level_inputs(lv)
+    ol = O.LevelInputs(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"], mlp)
+    oR, oT, oW = O.lm_solve([ol], 3, sc.R0.double(), sc.T0.double(), sc.W0.double(), O.IterOptions(l2_regularizer_base=1000.0))
+    packed = ops.pack_mlp([(w.float(), b.float()) for w, b in mlp]).cuda()
+    R, T, W, status = ops.lm_run([_level(ops, lv)], 3, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(sc.W0), mlp_packed=[packed],
+                                 l2_regularizer_base=1000.0)
+    assert status.abs().max().item() == 0
+    assert rel_fro(R, oR) < TOL_OUT and rel_fro(T, oT) < TOL_OUT and rel_fro(W, oW) < TOL_OUT
+    depth = ops.depth_compose(to_cuda32(lv.D).reshape(1, -1), to_cuda32(lv.B), W)
+    assert rel_fro(depth, (a["D"] + a["B"] @ oW).reshape(1, -1)) < TOL_OUT
