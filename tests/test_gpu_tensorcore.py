@@ -156,3 +156,32 @@ def test_lm_build_tensorcore_long_tile_runs(prec, fly, grid):
     print(f"prec={prec} fly={fly} grid={grid}: relH={eH:.2e} relg={eg:.2e}")
     assert eH < tol and eg < tol
     assert rel_fro(H[:, :6, :6], Hs[:, :6, :6]) < 2e-5 and rel_fro(rbar, rbs) < 2e-5
+
+
+def test_cfg4_window_sparse_points_solve():
+    """BASELINE.json configs[3] shape, scaled to test size: a keyframe tracked against 4 frames = 4 independent pairs (the reference
+    has no joint multi-view solve) on 4096 random sub-pixel points (seq_example.py:12), K=128, 10 LM iterations at a
+    fixed lambda, through the tensor-core kernel's ragged (non-grid) path.  FP32 and TF32X3 must meet the north-star tolerance
+    (or twice the float32 oracle's own error where the problem is too ill-conditioned for fp32); the faster modes are printed."""
+    from banet_b200 import ops
+    sc = scene_case(nb=4, H=240, W=320, C=64, K=128, level_ids=(3,), seed=404, n_points=4096, dtype=torch.float32)
+    lv = sc.levels[0]
+    level = [ops.Level(to_cuda32(lv.conv1), to_cuda32(lv.conv2), to_cuda32(lv.intr), to_cuda32(lv.p), to_cuda32(lv.D), to_cuda32(lv.B))]
+
+    def oracle(dtype):
+        a = oracle_level_inputs(lv, dtype)
+        ol = [O.LevelInputs(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"], [])]
+        return O.lm_solve(ol, 10, sc.R0.to(dtype), sc.T0.to(dtype), sc.W0.to(dtype), O.IterOptions(lambda_override=torch.full((4,), 0.5, dtype=dtype)))
+
+    oR, oT, oW = oracle(torch.float64)
+    fR, fT, fW = oracle(torch.float32)
+    floor = (rel_fro(fR, oR), rel_fro(fT, oT), rel_fro(fW, oW))
+    print(f"oracle fp32 vs fp64 (noise floor): {floor[0]:.2e} {floor[1]:.2e} {floor[2]:.2e}")
+    for prec in (0, 3, 2, 1):
+        R, T, W, status = ops.lm_run(level, 10, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(sc.W0), lambda_fixed=0.5, precision=prec)
+        errs = (rel_fro(R, oR), rel_fro(T, oT), rel_fro(W, oW))
+        print(f"prec={prec}: rel-fro R,T,W = {errs[0]:.2e} {errs[1]:.2e} {errs[2]:.2e}")
+        assert status.abs().max().item() == 0
+        if prec in (0, 3):
+            for e, f in zip(errs, floor):
+                assert e < max(1e-4, 2.0 * f)
