@@ -37,9 +37,23 @@ static int check_level(const banet_level_t* lv, const char* who)
     return BANET_OK;
 }
 
+// AUTO policy.  Default: TF32X2 wherever the tensor-core kernel applies.  Opt-in (BANET_AUTO_POLICY=levelwise; measured motivation
+// in DESIGN.md §4: the rounding error of H averages out as 1/sqrt(N), so the coarse levels carry nearly all of a solve's error and
+// nearly none of its time): TF32X3 (fp32-grade) below 65536 points per pair, single-pass TF32X1 above.  Not yet the default: the
+// combination has not been through the GPU parity suite.
+static bool auto_levelwise() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BANET_AUTO_POLICY"); v = (e && strcmp(e, "levelwise") == 0) ? 1 : 0; }
+    return v == 1;
+}
+
 int resolve_precision(const banet_level_t* lv, int precision)
 {
-    if (precision == BANET_PREC_AUTO) return tc_supported(lv) ? BANET_PREC_TF32X2 : BANET_PREC_FP32_SIMT;
+    if (precision == BANET_PREC_AUTO) {
+        if (!tc_supported(lv)) return BANET_PREC_FP32_SIMT;
+        if (auto_levelwise()) return lv->N < 65536 ? BANET_PREC_TF32X3 : BANET_PREC_TF32X1;
+        return BANET_PREC_TF32X2;
+    }
     if (precision == BANET_PREC_FP32_SIMT) return precision;
     if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2 || precision == BANET_PREC_TF32X3) {
         if (!tc_supported(lv)) {
