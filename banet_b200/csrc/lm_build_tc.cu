@@ -691,9 +691,19 @@ lm_build_tc_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_const
 }
 
 // ---- host side ------------------------------------------------------------------------------------
+// tuning knob (not part of the ABI yet): BANET_TC_SMALLK=1 lets K = 64 / 32 take the generation-6 tensor-core kernel too
+// (two-pass and fp32-grade modes; TF32X1 falls back to TF32X2).  Off by default: not yet through the GPU parity suite.
+static bool tc_small_k() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("BANET_TC_SMALLK"); v = (e && atoi(e) == 1) ? 1 : 0; }
+    return v == 1;
+}
+static int tc_generation();
+
 bool tc_supported(const banet_level_t* lv)
 {
-    return lv->K == TC_K && (lv->C == 64 || lv->C == 128) && (lv->conv2_channels == lv->C || lv->conv2_channels == 3 * lv->C) &&
+    const bool k_ok = lv->K == TC_K || (tc_small_k() && tc_generation() == 6 && (lv->K == 64 || lv->K == 32));
+    return k_ok && (lv->C == 64 || lv->C == 128) && (lv->conv2_channels == lv->C || lv->conv2_channels == 3 * lv->C) &&
            ((reinterpret_cast<uintptr_t>(lv->conv1) | reinterpret_cast<uintptr_t>(lv->conv2) | reinterpret_cast<uintptr_t>(lv->B)) % 16 == 0) &&
            (long long)lv->nb * lv->N < (1LL << 31) && (long long)lv->nb * ((lv->N + 63) / 64 + 80) < (1LL << 31);
 }
@@ -716,7 +726,7 @@ int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan)
     return BANET_OK;
 }
 
-int lm_build_tc6_launch(int mode, bool fly, int nch, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st);
+int lm_build_tc6_launch(int mode, bool fly, int nch, int kblk, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st);
 // tuning knob (not part of the ABI): BANET_TC_GEN=5 selects the previous kernel generation (default 6: helper warpgroup)
 static int tc_generation() {
     static int gen = 0;
@@ -763,8 +773,8 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
                   "lm_build (tensor-core path) needs K=128, C in {64,128}, 16-B aligned tensors; got K=%d C=%d", lv->K, lv->C);
     CUtensorMap tm;
     int rc;
-    if (lv->grid_w > 0) rc = make_tmap_f32_3d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->grid_h, lv->grid_w, TC_K, 8, 8, 32);
-    else rc = make_tmap_f32_2d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->N, TC_K, TC_TILE, 32);
+    if (lv->grid_w > 0) rc = make_tmap_f32_3d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->grid_h, lv->grid_w, lv->K, 8, 8, 32);
+    else rc = make_tmap_f32_2d_sw128_32b(&tm, lv->B, (uint64_t)lv->nb * lv->N, lv->K, TC_TILE, 32);
     if (rc) return rc;
     const bool fly = lv->conv2_channels == lv->C;
     CUtensorMap tm2;        // conv2 footprint prefetch boxes: C channels x (12|14)^2 texels
@@ -783,7 +793,7 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     { const char* e = getenv("BANET_TC_PF_TAPS"); prm.pf_taps = (e && atoi(e) == 1) ? 1 : 0; }
     { const char* e = getenv("BANET_TC_TRACE_PTR"); prm.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 0)) : nullptr; }
     const int nch = lv->C / 64;
-    if (tc_generation() == 6) rc = lm_build_tc6_launch(mode, fly, nch, tm, prm, plan.grid, st);
+    if (tc_generation() == 6) rc = lm_build_tc6_launch(lv->K == TC_K ? mode : (mode == 3 ? 3 : 2), fly, nch, lv->K / 32, tm, prm, plan.grid, st);
     else if (nch == 2) rc = fly ? launch_tc_mode<2, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<2, false>(mode, tm, tm2, prm, plan.grid, st);
     else          rc = fly ? launch_tc_mode<1, true>(mode, tm, tm2, prm, plan.grid, st) : launch_tc_mode<1, false>(mode, tm, tm2, prm, plan.grid, st);
     if (rc) return rc;

@@ -86,12 +86,15 @@ __device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long lon
     return tc;
 }
 
-template <int NCH, bool FLY, int MODE>
+template <int NCH, bool FLY, int MODE, int KBLK = 4>
 __global__ void __launch_bounds__(THREADS, 1)
 lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams prm)
 {
     using SM = Smem<MODE, FLY>;
     constexpr int NST = SM::NST, NREC = SM::NREC;
+    // KBLK = K / 32 basis blocks actually present (K = 128, 64 or 32).  The smem / TMEM geometry stays that of K = 128 (M = 128 rows of D,
+    // 32-KB stages); blocks >= KBLK are never loaded, read by the SIMT loops or drained, and the [v | t] block of R follows the last one.
+    constexpr int KR = 32 * KBLK, EXTB = KBLK, NMMA = KBLK == 4 ? NN : KR + 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align through the 32-bit shared address so that the compiler keeps every access in the shared state space (LDS/STS, not generic LD/ST)
     unsigned char* base = smem_raw + (SM::slack ? ((512u - (smem_u32(smem_raw) & 511u)) & 511u) : 0u);
@@ -136,8 +139,8 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
     if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
     for (int i = tid; i < TILE * 8; i += THREADS) {       // pad chunks of R / R_lo's 5th block stay zero
         const int r = i >> 3, c = i & 7;
-        *reinterpret_cast<float4*>(base + SM::off_R + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == 3) *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(base + SM::off_R + EXTB * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODE == 3) *reinterpret_cast<float4*>(base + SM::off_Rlo + EXTB * 8192 + sw128_32b_off(r, c)) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     fence_proxy_async_smem();
     tc_fence_before_sync();
@@ -198,10 +201,11 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 if (lane < 9) myPose[lane] = prm.R[b * 9 + lane];
                 else if (lane < 12) myPose[lane] = prm.T[b * 3 + lane - 9];
                 else if (lane < 16) myPose[lane] = prm.intr[b * 4 + lane - 12];
-                *reinterpret_cast<float4*>(myW + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KB + 4 * lane));
+                if (KBLK == 4 || 4 * lane < KR)
+                    *reinterpret_cast<float4*>(myW + 4 * lane) = __ldg(reinterpret_cast<const float4*>(prm.W + (size_t)b * KR + 4 * lane));
                 if constexpr (MODE == 1)     // a pure function of the inputs that changes whenever the iterate changes (see the rounding below)
-                    dseed = (__float_as_uint(__ldg(prm.W + (size_t)b * KB)) * 0x9E3779B1u) ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KB + 1)) * 0x85EBCA77u)
-                          ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KB + 2)) * 0xC2B2AE3Du) ^ __float_as_uint(__ldg(prm.T + b * 3)) ^ (uint32_t)b;
+                    dseed = (__float_as_uint(__ldg(prm.W + (size_t)b * KR)) * 0x9E3779B1u) ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KR + 1)) * 0x85EBCA77u)
+                          ^ (__float_as_uint(__ldg(prm.W + (size_t)b * KR + 2)) * 0xC2B2AE3Du) ^ __float_as_uint(__ldg(prm.T + b * 3)) ^ (uint32_t)b;
                 __syncwarp();
             }
             const int s = j % NST, sr = j % NREC;
@@ -226,6 +230,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int blk = 2 * hf + (i >> 3), c = ((i & 7) + r16) & 7;
+                    if (KBLK != 4 && blk >= KBLK) continue;
                     const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nlr, c));
                     const float4 w4 = *reinterpret_cast<const float4*>(myW + blk * 32 + c * 4);
                     acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
@@ -409,7 +414,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         const int awi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*awi .. 16*awi+15
         const int atid = tid - (W0 + GW) * 32;
         const int nlr = awi * 16 + r16;
-        const SlotLayout L{KB, C};
+        const SlotLayout L{KR, C};
         unsigned char* Rs = base + SM::off_R;
         float cc[28];
 #pragma unroll
@@ -418,7 +423,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         float fx = 0.f, fy = 0.f;
         int rr = (ntiles > 0) ? (int)((unsigned)t_begin % (unsigned)prm.tiles_per_pair) : 0;
         // issuer state (kept by every lane of warp 0, used by its lane 0)
-        constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, NN);
+        constexpr uint32_t idesc = make_idesc_tf32_mn_mn(128, NMMA);
         int chain = -1, tic = 0, set = 0, mspan = 0;
         bool new_span = true;
         uint32_t accH = 0, accL = 0;
@@ -426,15 +431,15 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         auto issue_tma = [&](int t) {                        // basis tile t -> stage t % NST (elected thread)
             const int st = t % NST;
             const TileCoord tc = tile_coord(prm, t_begin + t);
-            mbar_arrive_expect_tx(&fullB[st], STAGE_A);
+            mbar_arrive_expect_tx(&fullB[st], KBLK * 8192);
             unsigned char* dst = base + SM::off_A + st * STAGE_A;
             if (grid2d) {
 #pragma unroll
-                for (int blk = 0; blk < 4; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[st]);
+                for (int blk = 0; blk < KBLK; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[st]);
             } else {
                 const int row = tc.b * N + tc.n0;
 #pragma unroll
-                for (int blk = 0; blk < 4; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[st]);
+                for (int blk = 0; blk < KBLK; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[st]);
             }
         };
         auto flush = [&](int sp) {
@@ -516,11 +521,11 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             if (lane < 16) {                                 // R columns 128..134 = [v(6) | t], column 135 stays zero
                 const float4 e0 = make_float4(tf32_rna(ext[0]), tf32_rna(ext[1]), tf32_rna(ext[2]), tf32_rna(ext[3]));
                 const float4 e1 = make_float4(tf32_rna(ext[4]), tf32_rna(ext[5]), tf32_rna(ext[6]), 0.f);
-                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nlr, 0)) = e0;
-                *reinterpret_cast<float4*>(Rs + 4 * 8192 + sw128_32b_off(nlr, 1)) = e1;
+                *reinterpret_cast<float4*>(Rs + EXTB * 8192 + sw128_32b_off(nlr, 0)) = e0;
+                *reinterpret_cast<float4*>(Rs + EXTB * 8192 + sw128_32b_off(nlr, 1)) = e1;
                 if constexpr (MODE == 3) {
-                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nlr, 0)) = make_float4(ext[0] - e0.x, ext[1] - e0.y, ext[2] - e0.z, ext[3] - e0.w);
-                    *reinterpret_cast<float4*>(base + SM::off_Rlo + 4 * 8192 + sw128_32b_off(nlr, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + EXTB * 8192 + sw128_32b_off(nlr, 0)) = make_float4(ext[0] - e0.x, ext[1] - e0.y, ext[2] - e0.z, ext[3] - e0.w);
+                    *reinterpret_cast<float4*>(base + SM::off_Rlo + EXTB * 8192 + sw128_32b_off(nlr, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
                 }
             }
             // R rows (and the split parts): elementwise on the lane's half row, so walk the PHYSICAL 16-B slots (rotated by the row: every
@@ -528,6 +533,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             const uint32_t rowoff = hf * 16384 + nlr * 128;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
+                if (KBLK != 4 && 2 * hf + (i >> 3) >= KBLK) continue;
                 const uint32_t off = rowoff + (i >> 3) * 8192 + (((i & 7) + r16) & 7) * 16;
                 const float4 bv = *reinterpret_cast<const float4*>(As + off);
                 const float4 pv = make_float4(sn * bv.x, sn * bv.y, sn * bv.z, sn * bv.w);
@@ -575,30 +581,31 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         // ===================================================================== drainer warps: TMEM -> partial slots, fully asynchronous
         setmaxnreg_dec<40>();
         const int dq = warp - (W0 + GW + AW);                // TMEM lane quadrant (= warp % 4)
-        const SlotLayout L{KB, C};
+        const SlotLayout L{KR, C};
         auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
             const int row = dq * 32 + lane;
+            if (KBLK != 4 && dq * 32 >= KR) return;          // this lane quadrant holds no basis row (warp-uniform)
             const uint32_t tq = tmem + ((uint32_t)(dq * 32) << 16) + col0;
             float v[16];
 #pragma unroll 1
-            for (int cb = 0; cb < 8; ++cb) {
+            for (int cb = 0; cb < KR / 16; ++cb) {
                 tmem_ld_32x16(tq + cb * 16, v);
-                float* dst = slot + (size_t)(cb * 16) * KB + row;
+                float* dst = slot + (size_t)(cb * 16) * KR + row;
                 if (overwrite) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KB] = v[j];
+                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = v[j];
                 } else {
                     float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)j * KB];
+                    for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)j * KR];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KB] = o[j] + v[j];
+                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = o[j] + v[j];
                 }
             }
-            tmem_ld_32x16(tq + 128, v);
+            tmem_ld_32x16(tq + KR, v);
             float* dst = slot + L.off_ext() + row;
 #pragma unroll
-            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KB] = v[r]; else dst[r * KB] += v[r]; }
+            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KR] = v[r]; else dst[r * KR] += v[r]; }
         };
         int chain = -1, tic = 0, span = 0, cur_b = -1;
         bool first = true;
@@ -642,10 +649,10 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
     if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
-template <int NCH, bool FLY, int MODE>
+template <int NCH, bool FLY, int MODE, int KBLK = 4>
 static int launch6(const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
 {
-    auto kern = lm_build_tc6_kernel<NCH, FLY, MODE>;
+    auto kern = lm_build_tc6_kernel<NCH, FLY, MODE, KBLK>;
     const int smem = Smem<MODE, FLY>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("lm_build_tc6: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return BANET_ERR_CUDA; }
@@ -654,8 +661,12 @@ static int launch6(const CUtensorMap& tm, const BuildParams& prm, int grid, cuda
     return BANET_OK;
 }
 template <int NCH, bool FLY>
-static int launch6_mode(int mode, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+static int launch6_mode(int mode, int kblk, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
 {
+    if (kblk != 4) {             // K = 64 / 32 (opt-in, BANET_TC_SMALLK=1): instantiated for the two-pass and the fp32-grade mode only
+        if (kblk == 2) return mode == 3 ? launch6<NCH, FLY, 3, 2>(tm, prm, grid, st) : launch6<NCH, FLY, 2, 2>(tm, prm, grid, st);
+        return mode == 3 ? launch6<NCH, FLY, 3, 1>(tm, prm, grid, st) : launch6<NCH, FLY, 2, 1>(tm, prm, grid, st);
+    }
     if (mode == 1) return launch6<NCH, FLY, 1>(tm, prm, grid, st);
     if (mode == 2) return launch6<NCH, FLY, 2>(tm, prm, grid, st);
     return launch6<NCH, FLY, 3>(tm, prm, grid, st);
@@ -663,10 +674,10 @@ static int launch6_mode(int mode, const CUtensorMap& tm, const BuildParams& prm,
 
 }  // namespace v6
 
-int lm_build_tc6_launch(int mode, bool fly, int nch, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
+int lm_build_tc6_launch(int mode, bool fly, int nch, int kblk, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st)
 {
-    if (nch == 2) return fly ? v6::launch6_mode<2, true>(mode, tm, prm, grid, st) : v6::launch6_mode<2, false>(mode, tm, prm, grid, st);
-    return fly ? v6::launch6_mode<1, true>(mode, tm, prm, grid, st) : v6::launch6_mode<1, false>(mode, tm, prm, grid, st);
+    if (nch == 2) return fly ? v6::launch6_mode<2, true>(mode, kblk, tm, prm, grid, st) : v6::launch6_mode<2, false>(mode, kblk, tm, prm, grid, st);
+    return fly ? v6::launch6_mode<1, true>(mode, kblk, tm, prm, grid, st) : v6::launch6_mode<1, false>(mode, kblk, tm, prm, grid, st);
 }
 
 }  // namespace banet
