@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libbanet_sm100.so")
 
 BANET_OK = 0
-PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2, PREC_TF32X3 = -1, 0, 1, 2, 3
+PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2, PREC_TF32X3, PREC_TF32_LEVELWISE = -1, 0, 1, 2, 3, 4
 
 c_float_p = C.c_void_p      # raw device pointers
 c_stream = C.c_void_p
@@ -32,6 +32,11 @@ class BanetSolveOpts(C.Structure):
     _fields_ = [("damping_eps", C.c_float), ("undamped_last", C.c_int), ("vmatrix_batch_scramble", C.c_int)]
 
 
+class BanetTuning(C.Structure):
+    """struct banet_tuning (include/banet_abi.h): diagnostic knobs, defaults = production."""
+    _fields_ = [("tc_generation", C.c_int), ("tc7_force_direct", C.c_int), ("tc7_band_rows", C.c_int)]
+
+
 class BanetError(RuntimeError):
     pass
 
@@ -42,6 +47,8 @@ SIGNATURES = {
     "banet_last_error": (C.c_char_p, []),
     "banet_device_check": (C.c_int, []),
     "banet_num_sms": (C.c_int, []),
+    "banet_set_tuning": (C.c_int, [C.POINTER(BanetTuning)]),
+    "banet_get_tuning": (C.c_int, [C.POINTER(BanetTuning)]),
     "banet_eqc_workspace_bytes": (C.c_size_t, [C.c_int] * 4),
     "banet_eqc_fwd": (C.c_int, [c_float_p] * 3 + [C.c_int] * 4 + [c_float_p] * 2 + [C.c_void_p, C.c_size_t, c_stream]),
     "banet_eqc_bwd": (C.c_int, [c_float_p] * 5 + [C.c_int] * 5 + [c_float_p] * 3 + [c_stream]),
@@ -88,6 +95,12 @@ def check(rc: int, what: str) -> None:
     if rc != BANET_OK:
         msg = load().banet_last_error().decode("utf-8", "replace")
         raise BanetError(f"{what} failed (code {rc}): {msg}")
+
+
+def set_tuning(tc_generation: int = 0, tc7_force_direct: bool = False, tc7_band_rows: int = 4) -> None:
+    """Diagnostic knobs (process-wide); call with no arguments to restore the production defaults."""
+    t = BanetTuning(int(tc_generation), int(tc7_force_direct), int(tc7_band_rows))
+    check(load().banet_set_tuning(C.byref(t)), "banet_set_tuning")
 
 
 def require_device() -> None:

@@ -37,22 +37,20 @@ static int check_level(const banet_level_t* lv, const char* who)
     return BANET_OK;
 }
 
-// AUTO policy.  Default: TF32X2 wherever the tensor-core kernel applies.  Opt-in (BANET_AUTO_POLICY=levelwise; measured motivation
-// in DESIGN.md §4: the rounding error of H averages out as 1/sqrt(N), so the coarse levels carry nearly all of a solve's error and
-// nearly none of its time): TF32X3 (fp32-grade) below 65536 points per pair, single-pass TF32X1 above.  Not yet the default: the
-// combination has not been through the GPU parity suite.
-static bool auto_levelwise() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("BANET_AUTO_POLICY"); v = (e && strcmp(e, "levelwise") == 0) ? 1 : 0; }
-    return v == 1;
-}
+// Level-wise policy (BANET_PREC_TF32_LEVELWISE; measured motivation in DESIGN.md §4): the rounding error of H averages out as
+// 1/sqrt(N), so the coarse levels carry nearly all of a solve's error and nearly none of its time: TF32X3 (fp32-grade) below
+// 65536 points per pair, single-pass TF32X1 above.
+static int levelwise_mode(const banet_level_t* lv) { return lv->N < 65536 ? BANET_PREC_TF32X3 : BANET_PREC_TF32X1; }
 
 int resolve_precision(const banet_level_t* lv, int precision)
 {
     if (precision == BANET_PREC_AUTO) {
         if (!tc_supported(lv)) return BANET_PREC_FP32_SIMT;
-        if (auto_levelwise()) return lv->N < 65536 ? BANET_PREC_TF32X3 : BANET_PREC_TF32X1;
         return BANET_PREC_TF32X2;
+    }
+    if (precision == BANET_PREC_TF32_LEVELWISE) {
+        if (!tc_supported(lv)) return BANET_PREC_FP32_SIMT;
+        return levelwise_mode(lv);
     }
     if (precision == BANET_PREC_FP32_SIMT) return precision;
     if (precision == BANET_PREC_TF32X1 || precision == BANET_PREC_TF32X2 || precision == BANET_PREC_TF32X3) {
@@ -85,6 +83,22 @@ using namespace banet;
 extern "C" int banet_abi_version(void) { return BANET_ABI_VERSION; }
 extern "C" const char* banet_last_error(void) { return g_err; }
 extern "C" int banet_num_sms(void) { return num_sms(); }
+
+extern "C" int banet_set_tuning(const banet_tuning_t* t)
+{
+    const banet_tuning_t def = {0, 0, 4};
+    if (!t) { set_tuning(def); return BANET_OK; }
+    BANET_REQUIRE((t->tc_generation == 0 || t->tc_generation == 6 || t->tc_generation == 7) && t->tc7_band_rows >= 1, BANET_ERR_BAD_ARG,
+                  "set_tuning: tc_generation must be 0, 6 or 7 and tc7_band_rows >= 1");
+    set_tuning(*t);
+    return BANET_OK;
+}
+extern "C" int banet_get_tuning(banet_tuning_t* t)
+{
+    BANET_REQUIRE(t, BANET_ERR_BAD_ARG, "get_tuning: null");
+    *t = tuning();
+    return BANET_OK;
+}
 
 extern "C" int banet_device_check(void)
 {

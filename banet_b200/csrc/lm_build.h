@@ -10,11 +10,11 @@ struct BuildParams {
     float* partials;
     int slot_floats, max_span, tiles_per_pair;
     long long total_tiles;
-    int grid_w, grid_h, tiles_x;      // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
-    int hdd_transposed;
-    int pf_taps;                      // tuning (generation 5 only, BANET_TC_PF_TAPS=1): per-lane L2 prefetch of the next tile's tap lines; off: not a win
-    int pf_conv2;                     // tuning (generation 5 only, BANET_TC_PF_CONV2=1): predicted conv2-footprint L2 prefetch; off: not a win
-    long long* trace;                 // optional debug timeline buffer (NULL in production)               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
+    int grid_w, grid_h, tiles_x, tiles_y;   // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
+    int band_rows;                    // generation 7: tiles are walked in bands of this many tile rows, column by column inside a band
+    int hdd_transposed;               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
+    int force_direct;                 // generation 7, testing: take the global-tap fallback for every tile
+    long long* trace;                 // optional debug timeline buffer (NULL in production)
 };
 
 struct BuildPlan {
@@ -32,7 +32,10 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
 
 int launch_lm_reduce(const BuildParams& prm, int grid_build, float* H, float* g, float* rbar_sum, float* nvalid, cudaStream_t st);
 
-// tensor-core path (lm_build_tc.cu): K = 128, C in {64,128}
+// tensor-core path (lm_build_tc_host.cu + lm_build_tc6.cu / lm_build_tc7.cu): K in {32,64,128}, C in {64,128}
+void set_tuning(const banet_tuning_t& t);
+const banet_tuning_t& tuning();
+void lm_build_tc7_window(int* wx, int* wy);
 bool tc_supported(const banet_level_t* lv);
 int build_plan_tc(const banet_level_t* lv, int num_sms, BuildPlan* plan);
 int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const float* R, const float* T, const float* W,

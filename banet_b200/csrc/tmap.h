@@ -60,8 +60,8 @@ inline int make_tmap_f32_3d_sw128_32b(CUtensorMap* out, const float* base, uint6
     return BANET_OK;
 }
 
-// fp32 NHWC map [nb, h, w, c] for L2 prefetch boxes (no swizzle): box = box_c x box_w x box_h x 1.
-inline int make_tmap_f32_nhwc_prefetch(CUtensorMap* out, const float* base, uint64_t nb, uint64_t h, uint64_t w, uint64_t c,
+// fp32 NHWC map [nb, h, w, c], no swizzle: box = box_c x box_w x box_h x 1 (staged F2 windows: box_c = 32 channels = 128 B rows).
+inline int make_tmap_f32_nhwc(CUtensorMap* out, const float* base, uint64_t nb, uint64_t h, uint64_t w, uint64_t c,
                                        uint32_t box_c, uint32_t box_w, uint32_t box_h)
 {
     PFN_encodeTiled enc = get_encode_tiled();
@@ -71,9 +71,9 @@ inline int make_tmap_f32_nhwc_prefetch(CUtensorMap* out, const float* base, uint
     cuuint32_t box[4] = {box_c, box_w, box_h, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    BANET_REQUIRE(r == CUDA_SUCCESS, BANET_ERR_CUDA, "cuTensorMapEncodeTiled(nhwc prefetch) failed (%d)", (int)r);
+    BANET_REQUIRE(r == CUDA_SUCCESS, BANET_ERR_CUDA, "cuTensorMapEncodeTiled(nhwc) failed (%d)", (int)r);
     return BANET_OK;
 }
 

@@ -5,8 +5,10 @@
  * Conventions
  *   - every pointer is a DEVICE pointer (fp32 unless stated), row-major contiguous, laid out exactly
  *     like the reference tensors named beside it; `stream` is a cudaStream_t passed as void*;
- *   - the library allocates nothing and keeps no global state (contrast reference utils.cu:210-216,
- *     259-296: process-static persistent scratch); the caller owns outputs and workspaces;
+ *   - the library allocates nothing and hoards no scratch (contrast reference utils.cu:210-216,
+ *     259-296: process-static persistent scratch); the caller owns outputs and workspaces.  The only
+ *     process-wide state is the explicit diagnostic tuning struct below (banet_set_tuning; defaults
+ *     are the production path) and the thread-local error string; there are no environment knobs;
  *   - every call is asynchronous on `stream` and returns 0 (BANET_OK) or a negative error code;
  *     banet_last_error() gives a thread-local message (reference ignores BLAS status, utils.cu:331);
  *   - per-pair numeric trouble (non-positive pivot, NaN) is reported in a device-side `status[nb]`.
@@ -38,6 +40,16 @@ const char* banet_last_error(void);
 /* 0 if the current CUDA device can run this library (compute capability 10.x), else an error. */
 int         banet_device_check(void);
 int         banet_num_sms(void);
+
+/* Diagnostic / test knobs (process-wide; defaults = production).  Results never depend on them beyond
+ * fp32 summation order. */
+typedef struct banet_tuning {
+    int tc_generation;      /* 0: newest tensor-core build kernel that applies (7: TMA-staged F2 windows, else 6); 6: force generation 6 */
+    int tc7_force_direct;   /* 1: generation 7 takes its per-tile global-tap fallback for every tile (tests the fallback) */
+    int tc7_band_rows;      /* generation 7 walks the 8x8 tiles of a pair in bands of this many tile rows (L2 reuse of the window halos); default 4 */
+} banet_tuning_t;
+int banet_set_tuning(const banet_tuning_t* t);   /* NULL restores the defaults */
+int banet_get_tuning(banet_tuning_t* t);
 
 /* ------------------------------------------------------------------------------------------------
  * (1) Op level — the reference's own native boundary.
@@ -100,6 +112,7 @@ typedef struct banet_level {
 #define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32: basis truncated by the tensor core, s*b rounded to nearest */
 #define BANET_PREC_TF32X2    2   /* split-A two-pass tf32: b = trunc(b) + (b - trunc(b)); only s*b's rounding remains             */
 #define BANET_PREC_TF32X3    3   /* three passes: also s*b = hi + lo; the dropped lo*lo term is ~2^-22: fp32-grade sums          */
+#define BANET_PREC_TF32_LEVELWISE 4 /* per level: TF32X3 below 65536 points per pair, TF32X1 above (FP32_SIMT where tensor cores do not apply) */
 
 /* Normal equations + damping statistics of one iteration (bundlenet.py:206-239, 259-263 and the
  * mean-|diff| of :243), fused: J, G, d are never materialised.

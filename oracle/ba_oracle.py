@@ -28,15 +28,18 @@ SELU_SCALE = 1.0507009873554804934193349852946
 
 
 # --------------------------------------------------------------------------- SE(3) helpers
-def angle_axis_rotation(wx: Tensor, wy: Tensor, wz: Tensor) -> Tensor:
+def angle_axis_rotation(wx: Tensor, wy: Tensor, wz: Tensor, clamp: bool = True) -> Tensor:
     """bundlenet.py:17-37 `AngleaAxisRotation`.  Inputs [nb,1,1] -> [nb,3,3].
 
     theta is clamped to >= 1e-6 (:20); the nine entries are stacked on the last
     axis, reshaped to [-1,3,3] and TRANSPOSED (:37), which yields the standard
     Rodrigues matrix  I + sin(t)[k]x + (1-cos t)[k]x^2.
+    legacy/ba.py:60-80 is the same without the clamp (`clamp=False`).
     """
     ones = torch.ones_like(wx)
-    theta = torch.clamp(torch.sqrt(wx * wx + wy * wy + wz * wz), min=1e-6)
+    theta = torch.sqrt(wx * wx + wy * wy + wz * wz)
+    if clamp:
+        theta = torch.clamp(theta, min=1e-6)
     wx, wy, wz = wx / theta, wy / theta, wz / theta
     c, s = torch.cos(theta), torch.sin(theta)
     e = torch.stack([c + wx * wx * (ones - c),
@@ -396,6 +399,58 @@ def normal_equations_structured(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W,
     return H, g, rbar, nvalid
 
 
+def normal_equations_structured_chunked(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W,
+                                        guard_nonfinite: bool = False, chunk: int = 32768):
+    """`normal_equations_structured` over point chunks (same sums, bounded memory): lets the float64 oracle run the
+    BASELINE cfg2 level sizes (N = 307 200, C = K = 128) that the materialised J of bundlenet.py:259-261 cannot."""
+    nb, N, C = conv1.shape
+    H = g = None
+    rbar = torch.zeros(nb, 1, C, dtype=conv1.dtype)
+    nvalid = torch.zeros(nb, dtype=conv1.dtype)
+    for a in range(0, N, chunk):
+        b = min(N, a + chunk)
+        Hc, gc, rb, nv = normal_equations_structured(conv1[:, a:b], conv2, fx[:, a:b], fy[:, a:b], ox[:, a:b], oy[:, a:b],
+                                                     p[:, :, a:b], D[:, a:b], None if B is None else B[:, a:b], R, T, W,
+                                                     guard_nonfinite)
+        H = Hc if H is None else H + Hc
+        g = gc if g is None else g + gc
+        rbar += rb * float(b - a)                                    # structured() returns the chunk MEAN; keep the sum
+        nvalid += nv
+    return H, g, rbar / float(N), nvalid
+
+
+def iteration_structured(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, mlp_params,
+                         opts: IterOptions = IterOptions(), chunk: int = 32768):
+    """bundle_iteration / camera_iteration (bundlenet.py:193-278 / :122-191) with the normal equations taken from the
+    chunked block form; identical maths (tests/test_oracle_consistency.py), usable at full BASELINE sizes."""
+    nb = conv1.shape[0]
+    bundle = B is not None
+    AtA, Atb, avg_residual, _ = normal_equations_structured_chunked(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W,
+                                                                    opts.guard_nonfinite, chunk)
+    if opts.lambda_override is not None:
+        lam = opts.lambda_override.reshape(-1, 1, 1).to(conv1.dtype)
+    else:
+        lam = torch.pow(torch.linalg.norm(avg_residual, dim=-1, keepdim=True), 2.0 + lambda_mlp(avg_residual, mlp_params))
+        if bundle and opts.l2_regularizer_base is not None:
+            lam = opts.l2_regularizer_base * lam                     # :252-253 (CameraIteration ignores the base)
+    diag = torch.diagonal(AtA, dim1=-2, dim2=-1)
+    if bundle and opts.undamped_last:
+        dvec = torch.cat([diag[:, :-1] + opts.damping_eps, torch.zeros(nb, 1, dtype=diag.dtype)], dim=-1)   # :266
+    else:
+        dvec = diag + opts.damping_eps                               # :182
+    solution = torch.linalg.solve(AtA + torch.diag_embed(dvec * lam.reshape(nb, 1)), Atb)
+    Rn, Tn = _update(solution[:, :6, :], R, T, opts)
+    return (Rn, Tn, W + solution[:, 6:, :]) if bundle else (Rn, Tn, None)
+
+
+def lm_solve_structured(levels, iters_per_level: int, R, T, W=None, opts: IterOptions = IterOptions(), chunk: int = 32768):
+    """`lm_solve` through `iteration_structured` (bounded memory)."""
+    for lv in levels:
+        for _ in range(iters_per_level):
+            R, T, W = iteration_structured(lv.conv1, lv.conv2, lv.fx, lv.fy, lv.ox, lv.oy, lv.p, lv.D, lv.B, R, T, W, lv.mlp, opts, chunk)
+    return R, T, W
+
+
 # --------------------------------------------------------------------------- schedulers
 @dataclass
 class ResizeGeometry:
@@ -544,7 +599,7 @@ def legacy_camera_iteration2(conv1, conv2, fx, fy, ox, oy, p, D, R, T, mlp_param
         motion = torch.linalg.solve(r, q.transpose(-1, -2) @ Atb)
     else:
         motion = torch.linalg.inv(AtA) @ Atb
-    Rn, Tn = _update(motion, R, T, opts)
+    Rn, Tn = _legacy_update(motion, R, T, with_vmatrix=True)          # ba.py:297-302 (un-clamped AngleaAxisRotation :60-80)
     s2, mask2, num_valid2, *_ = residual(Rn, Tn)
     avg2 = (num_valid2 * (mask2 * (s2[:, :, 0:C] - conv1)).abs().mean(dim=1, keepdim=True)).mean()
     if bool(avg2 < residual_ratio * avg_scalar):                     # ba.py:343
@@ -552,3 +607,79 @@ def legacy_camera_iteration2(conv1, conv2, fx, fy, ox, oy, p, D, R, T, mlp_param
         return Rn, Tn, torch.linalg.norm(m[:3]), torch.linalg.norm(m[3:]), num_valid.squeeze()
     z = torch.zeros((), dtype=conv1.dtype)
     return R, T, z, z, num_valid.squeeze()
+
+
+def interpolate2d2(imgs: Tensor, p: Tensor) -> Tensor:
+    """legacy/utils_python.py:177-232 `interpolate2d2`: `interpolate2d` on points [nb,N,2] without the mask."""
+    return interpolate2d(imgs, p[:, :, 0], p[:, :, 1])[0]
+
+
+def _legacy_update(motion, R, T, with_vmatrix: bool):
+    """legacy/ba.py:208-213 (`CameraIteration`: T' = t + dr T) and :297-302 (`CameraIteration2`: T' = V t + dr T); un-clamped rotation."""
+    wx, wy, wz, tx, ty, tz = [motion[:, i:i + 1, :] for i in range(6)]       # tf.unstack(axis=1) -> [nb,1] each; same values
+    dr = angle_axis_rotation(wx, wy, wz, clamp=False)
+    dt = torch.cat([tx, ty, tz], dim=1)
+    if with_vmatrix:
+        dt = v_matrix(wx, wy, wz) @ dt
+    return dr @ R, dt + dr @ T
+
+
+def legacy_camera_iteration(conv1, conv2, fx, fy, ox, oy, p, D, R, T, use_qr: bool = True):
+    """legacy/ba.py:147-214 `Tracker.CameraIteration`: pose-only step, lambda = ||rbar||^2 (no MLP, :190), normal equations as plain
+    matmuls + reduce_sum (:197-198, the in-repo statement of the custom op), QR solve (:203-206), T' = t + dr T (no V matrix, :213).
+    Returns (R', T', valid_fraction)."""
+    C = conv1.shape[2]; npix = conv1.shape[1]
+    Rp, x, y, Z, px, py = _warp(p, D, R, T, fx, fy, ox, oy)
+    s, _mask = interpolate2d(conv2, px, py)
+    mask = _mask.unsqueeze(-1)
+    diff = (s[:, :, 0:C] - conv1).unsqueeze(-1) @ mask
+    grad = torch.cat([s[:, :, C:2 * C].unsqueeze(-1) @ mask, s[:, :, 2 * C:3 * C].unsqueeze(-1) @ mask], -1)
+    avg_residual = diff.squeeze(-1).abs().mean(dim=1, keepdim=True)
+    lam = torch.pow(torch.linalg.norm(avg_residual, dim=-1, keepdim=True), 2.0)
+    J = camera_jacobian_matrix(x, y, Z, fx, fy, negate=False)
+    AtA = (J.transpose(-1, -2) @ ((grad.transpose(-1, -2) @ grad) @ J)).sum(dim=1)        # :197
+    Atb = (J.transpose(-1, -2) @ (grad.transpose(-1, -2) @ diff)).sum(dim=1)              # :198
+    diag = torch.diagonal(AtA, dim1=-2, dim2=-1)
+    AtA = AtA + torch.diag_embed(((diag.unsqueeze(-1) + 1e-5) @ lam).squeeze(-1))
+    if use_qr:
+        q, r = torch.linalg.qr(AtA, mode="complete")
+        motion = torch.linalg.solve(r, q.transpose(-1, -2) @ Atb)
+    else:
+        motion = torch.linalg.inv(AtA) @ Atb
+    Rn, Tn = _legacy_update(motion, R, T, with_vmatrix=False)
+    return Rn, Tn, mask.sum() / npix
+
+
+def legacy_track(intrisic, layers, points, d, initR, initT, level_iters, mlp_params_by_level, early_termination: bool = True,
+                 angle_change: float = 0.002 * (3.14 / 180.0), translation_change: float = 0.0002, residual_ratio: float = 1.0):
+    """legacy/ba.py:83-145 `Tracker.trackTF`: keyframe -> frame pose tracking over pyramid levels 1..3 (scale 2^(3-level)).
+    layers[l] is a 2-image batch (0 = keyframe, 1 = current frame, :112-113); un-normalised rays (:27-34); per level either
+    `level_iters[level-1]` plain CameraIterations (:117-121) or the early-terminated loop of CameraIteration2 (:123-141): continue
+    while iters < level_iters[level-1] and update_w > angle_change and update_t > translation_change (:132-133; a rejected step
+    returns 0 updates and therefore ends the level).  Returns (R, T, ratio) / (Rs, Ts, ratio) like the reference."""
+    npix = points.shape[1]
+    sfx, sfy = intrisic[:, 0].repeat(1, npix), intrisic[:, 1].repeat(1, npix)
+    sox, soy = intrisic[:, 2].repeat(1, npix), intrisic[:, 3].repeat(1, npix)
+    p = compute_coordinates(points, sfx, sfy, sox, soy, normalize=False)
+    R, T = initR, initT
+    rotations, translations = [initR], [initT]
+    ratio = torch.tensor(1.0, dtype=points.dtype)
+    for level in range(1, 4):
+        scale = 2 ** (3 - level)
+        fx, fy, ox, oy = sfx / scale, sfy / scale, sox / scale, soy / scale
+        layer1 = interpolate2d2(layers[level - 1][0:1], points / scale)                   # :112
+        layer2 = layers[level - 1][1:2]
+        layer2 = torch.cat([layer2, grad_fixed(layer2)], dim=-1)                          # :113-115
+        if not early_termination:
+            for _ in range(level_iters[level - 1]):
+                R, T, ratio = legacy_camera_iteration(layer1, layer2, fx, fy, ox, oy, p, d, rotations[-1], translations[-1])
+                rotations.append(R); translations.append(T)
+        else:
+            iters, update_w, update_t = 0, 1.0, 1.0
+            while iters < level_iters[level - 1] and angle_change < float(update_w) and translation_change < float(update_t):
+                R, T, update_w, update_t, ratio = legacy_camera_iteration2(layer1, layer2, fx, fy, ox, oy, p, d, R, T,
+                                                                           mlp_params_by_level[str(level)], residual_ratio)
+                iters += 1
+    if not early_termination:
+        return rotations[1:], translations[1:], ratio
+    return R, T, ratio

@@ -112,3 +112,19 @@ def test_golden_fixtures_match_oracle():
         for k in ref.files:
             if k.startswith("out_"):
                 assert np.allclose(out[k], ref[k], rtol=1e-10, atol=1e-12), (name, k)
+
+
+@pytest.mark.parametrize("K", [0, 5])
+def test_structured_chunked_solve_equals_materialised_solve(K):
+    """The bounded-memory whole-solve used as the checker at BASELINE sizes is the same maths as the reference-faithful one."""
+    sc = scene_case(nb=2, C=6, K=K, level_ids=(2, 3), seed=21)
+    olv = []
+    for lv in sc.levels:
+        a = oracle_level_inputs(lv)
+        olv.append(O.LevelInputs(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"], mlp_for(6, lv.level)))
+    W0 = None if K == 0 else sc.W0
+    R1, T1, W1 = O.lm_solve(olv, 2, sc.R0, sc.T0, W0)
+    R2, T2, W2 = O.lm_solve_structured(olv, 2, sc.R0, sc.T0, W0, chunk=500)
+    assert rel_fro(R2, R1) < 1e-11 and rel_fro(T2, T1) < 1e-10
+    if K:
+        assert rel_fro(W2, W1) < 1e-9
