@@ -49,7 +49,7 @@ class BundleNet(torch.nn.Module):
 
     def __init__(self, channels: int, levels: Sequence[str] = ("0", "1", "2", "3"), is_training: bool = True,
                  reuse_variables=None, vmatrix_batch_scramble: bool = False, precision: int = PREC_AUTO, seed: int = 7,
-                 exact_sym_grad: bool = False):
+                 exact_sym_grad: bool = False, training_path: str = "fused", strict_status: bool = False):
         super().__init__()
         self.is_training = is_training
         self.reuse_variables = reuse_variables
@@ -57,6 +57,12 @@ class BundleNet(torch.nn.Module):
         self.vmatrix_batch_scramble = vmatrix_batch_scramble
         self.precision = precision
         self.exact_sym_grad = exact_sym_grad      # False: the reference's op gradient 2*A*Ghat (utils.cu:648); True: A(Ghat+Ghat^T)
+        if training_path not in ("fused", "reference_split"):
+            raise ValueError("training_path must be 'fused' or 'reference_split'")
+        self.training_path = training_path        # fused: banet_lm_*_bwd kernels; reference_split: torch graph + native equation_construction
+        self.strict_status = strict_status
+        self.last_status: Optional[Tensor] = None
+        self.train(bool(is_training))
         self.geo = ResizeGeometry()
         g = torch.Generator().manual_seed(seed)
         dims = [channels, 2 * channels, 4 * channels, 2 * channels, channels, 1]
@@ -83,41 +89,61 @@ class BundleNet(torch.nn.Module):
         return ops.compute_coordinates(points2d, _intr_from_tiled(fx, fy, ox, oy), normalize=True)
 
     # ---- one LM iteration ----------------------------------------------------------------------
-    @staticmethod
-    def _wants_grad(*tensors) -> bool:
-        return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)
+    def _wants_grad(self, *tensors) -> bool:
+        """Gradients are recorded when autograd is on and a DATA input requires grad, or the module is in training mode (then the
+        lambda-MLP parameters do).  In eval mode with plain inputs the no-grad kernels run (same forward, nothing saved)."""
+        if not torch.is_grad_enabled():
+            return False
+        if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+            return True
+        return self.training and any(p.requires_grad for p in self.parameters())
 
-    def CameraIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, R, T, l2_regularizer_base=None, level=None,
-                        return_aux: bool = False, differentiable: Optional[bool] = None):
+    def _check_status(self, status: Tensor) -> None:
+        """Keeps the per-pair solver status of the last call (0 ok, 1 non-SPD matrix: step skipped, 2 non-finite input) in
+        `self.last_status` (device tensor, no host sync); `strict_status=True` turns a non-zero status into an exception."""
+        self.last_status = status
+        if self.strict_status and int(status.abs().max()) != 0:
+            raise RuntimeError(f"LM solve skipped a step for pairs {torch.nonzero(status).flatten().tolist()} (status {status.tolist()})")
+
+    def _iterate(self, conv1, conv2, intr, p, D, B, R, T, W, base, level, grid=None):
+        """One iteration, differentiable or not; returns (R', T', W', aux or None)."""
+        bundle = B is not None
+        if self._wants_grad(conv1, conv2, D, B, R, T, W):
+            if self.vmatrix_batch_scramble:
+                raise RuntimeError("vmatrix_batch_scramble=True (the reference's batch-interleaved VMatrix, bundlenet.py:45) is not differentiable here")
+            if self.training_path == "reference_split":
+                Rn, Tn, Wn = _ag.iteration(conv1, conv2, intr, p, D, B, R, T, W, self.mlp_params(str(level)), base if bundle else None,
+                                           exact_sym=self.exact_sym_grad)
+                return Rn, Tn, Wn, None
+            Rn, Tn, Wn, status = _ag.iteration_fused(conv1, conv2, intr, p, D, B, R, T, W, self.mlp_params(str(level)), base if bundle else None,
+                                                     exact_sym=self.exact_sym_grad, precision=self.precision, grid=grid, return_status=True)
+            self._check_status(status)
+            return Rn, Tn, Wn, None
+        lv = ops.Level(conv1, conv2, intr, p, D, B, grid=grid)
+        H, g, rbar, nvalid = ops.lm_build(lv, R, T, W, self.precision)
+        lam = ops.lm_lambda(rbar, conv1.shape[1], self.mlp_packed(str(level)), float(base) if bundle else 1.0)
+        Rn, Tn, Wn, delta, status = ops.lm_solve_update(H, g, lam, R, T, W, undamped_last=bundle, vmatrix_batch_scramble=self.vmatrix_batch_scramble)
+        self._check_status(status)
+        return Rn, Tn, Wn, dict(AtA=H, Atb=g, lam=lam, rbar_sum=rbar, nvalid=nvalid, solution=delta, status=status)
+
+    def CameraIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, R, T, l2_regularizer_base=None, level=None, return_aux: bool = False):
         """reference bundlenet.py:122-191 -> (updatedR, updatedT).  l2_regularizer_base accepted, unused (as there).
-        differentiable: None = automatically when gradients are being recorded (training path, banet_b200/autograd.py)."""
-        if differentiable or (differentiable is None and not return_aux and self._wants_grad(conv1, conv2, D, R, T, *self.parameters())):
-            Rn, Tn, _ = _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None, R, T, None,
-                                      self.mlp_params(str(level)), None, exact_sym=self.exact_sym_grad)
-            return Rn, Tn
-        lv = ops.Level(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None)
-        H, g, rbar, nvalid = ops.lm_build(lv, R, T, None, self.precision)
-        lam = ops.lm_lambda(rbar, conv1.shape[1], self.mlp_packed(str(level)), 1.0)
-        Rn, Tn, _, delta, status = ops.lm_solve_update(H, g, lam, R, T, None, undamped_last=False,
-                                                       vmatrix_batch_scramble=self.vmatrix_batch_scramble)
+        Differentiable (fused backward kernels) whenever gradients are being recorded; `return_aux` needs the no-grad path."""
         if return_aux:
-            return Rn, Tn, dict(AtA=H, Atb=g, lam=lam, rbar_sum=rbar, nvalid=nvalid, solution=delta, status=status)
+            with torch.no_grad():
+                Rn, Tn, _, aux = self._iterate(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None, R, T, None, 1.0, level)
+            return Rn, Tn, aux
+        Rn, Tn, _, _ = self._iterate(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, None, R, T, None, 1.0, level)
         return Rn, Tn
 
-    def BundleIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, l2_regularizer_base=None, level=None,
-                        return_aux: bool = False, differentiable: Optional[bool] = None):
+    def BundleIteration(self, conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, l2_regularizer_base=None, level=None, return_aux: bool = False):
         """reference bundlenet.py:193-278 -> (updatedR, updatedT, updatedW)."""
-        if differentiable or (differentiable is None and not return_aux and self._wants_grad(conv1, conv2, D, B, R, T, W, *self.parameters())):
-            return _ag.iteration(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B, R, T, W,
-                                 self.mlp_params(str(level)), l2_regularizer_base, exact_sym=self.exact_sym_grad)
-        lv = ops.Level(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B)
-        H, g, rbar, nvalid = ops.lm_build(lv, R, T, W, self.precision)
         base = 1.0 if l2_regularizer_base is None else float(l2_regularizer_base)      # :252-253
-        lam = ops.lm_lambda(rbar, conv1.shape[1], self.mlp_packed(str(level)), base)
-        Rn, Tn, Wn, delta, status = ops.lm_solve_update(H, g, lam, R, T, W, undamped_last=True,
-                                                        vmatrix_batch_scramble=self.vmatrix_batch_scramble)
         if return_aux:
-            return Rn, Tn, Wn, dict(AtA=H, Atb=g, lam=lam, rbar_sum=rbar, nvalid=nvalid, solution=delta, status=status)
+            with torch.no_grad():
+                Rn, Tn, Wn, aux = self._iterate(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B, R, T, W, base, level)
+            return Rn, Tn, Wn, aux
+        Rn, Tn, Wn, _ = self._iterate(conv1, conv2, _intr_from_tiled(fx, fy, ox, oy), p, D, B, R, T, W, base, level)
         return Rn, Tn, Wn
 
     # ---- level schedulers ----------------------------------------------------------------------
@@ -130,12 +156,15 @@ class BundleNet(torch.nn.Module):
         intr = torch.stack([geo.fx_num * k[:, 0] / geo.fx_den, geo.fy_num * k[:, 1] / geo.fy_den,
                             geo.fx_num * k[:, 2] / geo.fx_den - geo.ox_sub,
                             geo.fy_num * k[:, 3] / geo.fy_den - geo.oy_sub], dim=1).contiguous()
-        return _points, intr
+        return _points.detach(), intr.detach()
 
     def CameraResize(self, intrisic, layers, points, _depths, reuse_variables=False):
-        """reference bundlenet.py:280-329 -> (rotations, translations), levels 0..3 x 1 iteration."""
+        """reference bundlenet.py:280-329 -> (rotations, translations), levels 0..3 x 1 iteration.  Differentiable w.r.t. the feature
+        pyramid and the lambda-MLP parameters when gradients are being recorded (the depth is stop_gradient'ed, :288)."""
         nb = layers[-1].shape[0]
         _points, intr = self._prepare(intrisic, points)
+        grad = self._wants_grad(*layers)
+        resample, gfc = (_ag.resample, _ag.grad_fixed_concat) if grad else (ops.resample, ops.grad_fixed_concat)
         d = ops.resample(_depths.detach(), _points, 0.5)                       # :289-290
         p = ops.compute_coordinates(_points, intr, True)
         R = torch.eye(3, device=points.device).repeat(nb, 1, 1)
@@ -143,24 +172,24 @@ class BundleNet(torch.nn.Module):
         rotations, translations = [], []
         for level in range(0, 4):
             scale = 2 ** (3 - level)
-            layer1 = ops.resample(layers[level], _points, 1.0 / scale)         # :320
-            layer2 = ops.grad_fixed_concat(layers[level], swap_halves=True)    # :321-324
-            lv = ops.Level(layer1, layer2, intr / scale, p, d, None)
-            H, g, rbar, _ = ops.lm_build(lv, R, T, None, self.precision)
-            lam = ops.lm_lambda(rbar, _points.shape[1], self.mlp_packed(str(level)), 1.0)
-            R, T, _, _, _ = ops.lm_solve_update(H, g, lam, R, T, None, undamped_last=False,
-                                                vmatrix_batch_scramble=self.vmatrix_batch_scramble)
+            layer1 = resample(layers[level], _points, 1.0 / scale)             # :320
+            layer2 = gfc(layers[level], swap_halves=True)                      # :321-324
+            R, T, _, _ = self._iterate(layer1, layer2, intr / scale, p, d, None, R, T, None, 1.0, level)
             rotations.append(R); translations.append(T)
         return rotations, translations
 
     def BundleResize(self, intrisic, layers, points, basis, init_depth, init_rotation=None, init_translation=None,
                      reuse_variables=False):
-        """reference bundlenet.py:332-399 -> (output_rotations, output_translations, output_depths), levels 2,3."""
+        """reference bundlenet.py:332-399 -> (output_rotations, output_translations, output_depths), levels 2,3.  Differentiable w.r.t.
+        the feature pyramid, the basis, the initial pose and the lambda-MLP parameters when gradients are being recorded
+        (init_depth enters the LM only through stop_gradient, :341, and the output depth directly, :397)."""
         nb = layers[-1].shape[0]
         K = basis.shape[-1]
         _points, intr = self._prepare(intrisic, points)
+        grad = self._wants_grad(*layers, basis, init_depth, init_rotation, init_translation)
+        resample, gfc, compose = (_ag.resample, _ag.grad_fixed_concat, _ag.depth_compose) if grad else (ops.resample, ops.grad_fixed_concat, ops.depth_compose)
         d = ops.resample(init_depth.detach(), _points, 0.5)                    # :341-343
-        b = ops.resample(basis, _points, 0.5)                                  # :344
+        b = resample(basis, _points, 0.5)                                      # :344
         p = ops.compute_coordinates(_points, intr, True)                       # :358
         dev = points.device
         R = torch.eye(3, device=dev).repeat(nb, 1, 1) if init_rotation is None else init_rotation
@@ -170,14 +199,10 @@ class BundleNet(torch.nn.Module):
         Rs, Ts, Ds = [], [], []
         for level in range(2, 4):                                              # :376
             scale = 2 ** (3 - level)
-            layer1 = ops.resample(layers[level], _points, 1.0 / scale)         # :385
-            layer2 = ops.grad_fixed_concat(layers[level], swap_halves=True)    # :386-389
-            lv = ops.Level(layer1, layer2, intr / scale, p, d, b)
-            H, g, rbar, _ = ops.lm_build(lv, R, T, W, self.precision)
-            lam = ops.lm_lambda(rbar, _points.shape[1], self.mlp_packed(str(level)), 1000.0)   # :393
-            R, T, W, _, _ = ops.lm_solve_update(H, g, lam, R, T, W, undamped_last=True,
-                                                vmatrix_batch_scramble=self.vmatrix_batch_scramble)
+            layer1 = resample(layers[level], _points, 1.0 / scale)             # :385
+            layer2 = gfc(layers[level], swap_halves=True)                      # :386-389
+            R, T, W, _ = self._iterate(layer1, layer2, intr / scale, p, d, b, R, T, W, 1000.0, level)   # :393
             Rs.append(R); Ts.append(T)
-            depth = ops.depth_compose(init_depth.reshape(nb, -1), basis.reshape(nb, -1, K), W)   # :397
+            depth = compose(init_depth.reshape(nb, -1), basis.reshape(nb, -1, K), W)   # :397
             Ds.append(depth.reshape(nb, oh, ow, 1))
         return Rs, Ts, Ds

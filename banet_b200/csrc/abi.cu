@@ -170,6 +170,26 @@ extern "C" int banet_lm_solve_update(const float* H, const float* g, const float
     return lm_solve_update(H, g, lambda, nb, K, *opts, R, T, W, R_out, T_out, W_out, delta, status, 0, (cudaStream_t)stream);
 }
 
+extern "C" int banet_lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W,
+                                  const float* dH, const float* dg, const float* drbar_sum, int exact_sym,
+                                  float* dconv1, float* dconv2, float* dD, float* dB, float* dR, float* dT, float* dW, banet_stream_t stream)
+{
+    int rc = check_level(lv, "lm_build_bwd");
+    if (rc) return rc;
+    BANET_REQUIRE(R && T && dH && dg && drbar_sum && dconv1 && dconv2 && dD && dR && dT, BANET_ERR_BAD_ARG, "lm_build_bwd: null pointer");
+    BANET_REQUIRE(lv->K == 0 || (W && dB && dW), BANET_ERR_BAD_ARG, "lm_build_bwd: K=%d but W / dB / dW is null", lv->K);
+    return lm_build_bwd(lv, R, T, W, dH, dg, drbar_sum, exact_sym, dconv1, dconv2, dD, dB, dR, dT, dW, (cudaStream_t)stream);
+}
+
+extern "C" int banet_lm_solve_update_bwd(const float* H, const float* g, const float* lambda, const float* delta, int nb, int K, const banet_solve_opts_t* opts,
+                                         const float* R, const float* T, const float* dR_out, const float* dT_out, const float* dW_out,
+                                         float* dH, float* dg, float* dlambda, float* dR, float* dT, float* dW, banet_stream_t stream)
+{
+    BANET_REQUIRE(H && g && lambda && delta && opts && R && T && dR_out && dT_out && dH && dg && dlambda && dR && dT, BANET_ERR_BAD_ARG, "lm_solve_update_bwd: null pointer");
+    BANET_REQUIRE(nb > 0 && K >= 0 && (K == 0 || (dW_out && dW)), BANET_ERR_BAD_ARG, "lm_solve_update_bwd: bad shape nb=%d K=%d", nb, K);
+    return lm_solve_update_bwd(H, g, lambda, delta, nb, K, *opts, R, T, dR_out, dT_out, dW_out, dH, dg, dlambda, dR, dT, dW, (cudaStream_t)stream);
+}
+
 // -------------------------------------------------------------------------------------------------
 // whole solve
 namespace {

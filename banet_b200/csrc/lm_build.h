@@ -53,4 +53,11 @@ int lm_solve_update(const float* H, const float* g, const float* lambda, int nb,
                     const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
                     float* delta, int32_t* status, int status_accumulate, cudaStream_t st);
 
+// backward of one iteration (lm_bwd.cu)
+int lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W, const float* dH, const float* dg, const float* drbar,
+                 int exact_sym, float* dconv1, float* dconv2, float* dD, float* dB, float* dR, float* dT, float* dW, cudaStream_t st);
+int lm_solve_update_bwd(const float* H, const float* g, const float* lambda, const float* delta, int nb, int K, const banet_solve_opts_t& opts,
+                        const float* R, const float* T, const float* gRn, const float* gTn, const float* gWn,
+                        float* dH, float* dg, float* dlambda, float* dR, float* dT, float* dW, cudaStream_t st);
+
 }  // namespace banet

@@ -263,3 +263,68 @@ def lm_run_workspace_bytes(levels: Sequence[Level], precision: int = _lib.PREC_A
     structs = [lv.as_struct()[0] for lv in levels]
     arr = (BanetLevel * len(structs))(*structs)
     return int(lib.banet_lm_run_workspace_bytes(arr, len(structs), precision))
+
+
+# ------------------------------------------------------------------------------------------ backward of one iteration
+def lm_build_bwd(level: Level, R: Tensor, T: Tensor, W: Optional[Tensor], dH: Tensor, dg: Tensor, drbar_sum: Tensor, exact_sym: bool = False):
+    """Backward of lm_build (banet_lm_build_bwd) -> dconv1, dconv2, dD, dB, dR, dT, dW.  conv2 must be the 3C layout."""
+    lib = load()
+    st, keep = level.as_struct()
+    nb, K, Cc, N = st.nb, st.K, st.C, st.N
+    P = 6 + K
+    R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1))
+    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1))
+    dH = _chk(dH, "dH", (nb, P, P)); dg = _chk(dg.reshape(nb, P), "dg", (nb, P)); dr = _chk(drbar_sum, "drbar_sum", (nb, Cc))
+    dev = R.device
+    dconv1 = torch.empty(nb, N, Cc, device=dev); dconv2 = torch.empty(nb, st.h, st.w, 3 * Cc, device=dev)
+    dD = torch.empty(nb, N, 1, device=dev); dB = None if K == 0 else torch.empty(nb, N, K, device=dev)
+    dR = torch.empty(nb, 3, 3, device=dev); dT = torch.empty(nb, 3, 1, device=dev); dW = None if K == 0 else torch.empty(nb, K, 1, device=dev)
+    check(lib.banet_lm_build_bwd(C.byref(st), R.data_ptr(), T.data_ptr(), _ptr(Wt), dH.data_ptr(), dg.data_ptr(), dr.data_ptr(), int(bool(exact_sym)),
+                                 dconv1.data_ptr(), dconv2.data_ptr(), dD.data_ptr(), _ptr(dB), dR.data_ptr(), dT.data_ptr(), _ptr(dW), _stream()),
+          "banet_lm_build_bwd")
+    return dconv1, dconv2, dD, dB, dR, dT, dW
+
+
+def lm_solve_update_bwd(H: Tensor, g: Tensor, lam: Tensor, delta: Tensor, R: Tensor, T: Tensor, dRn: Tensor, dTn: Tensor, dWn: Optional[Tensor],
+                        damping_eps: float = 1e-5, undamped_last: bool = True):
+    """Backward of lm_solve_update (banet_lm_solve_update_bwd) -> dH, dg, dlambda, dR, dT, dW."""
+    lib = load()
+    Hc = _chk(H, "H"); nb, P, _ = Hc.shape
+    K = P - 6
+    gc = _chk(g.reshape(nb, P), "g", (nb, P)); lc = _chk(lam.reshape(nb), "lambda", (nb,)); dl = _chk(delta, "delta", (nb, P))
+    R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1))
+    gR = _chk(dRn, "dR_out", (nb, 3, 3)); gT = _chk(dTn, "dT_out", (nb, 3, 1)); gW = None if K == 0 else _chk(dWn, "dW_out", (nb, K, 1))
+    dev = Hc.device
+    dH = torch.empty(nb, P, P, device=dev); dg = torch.empty(nb, P, device=dev); dlam = torch.empty(nb, device=dev)
+    dR = torch.empty(nb, 3, 3, device=dev); dT = torch.empty(nb, 3, 1, device=dev); dW = None if K == 0 else torch.empty(nb, K, 1, device=dev)
+    opts = BanetSolveOpts(float(damping_eps), int(undamped_last), 0)
+    check(lib.banet_lm_solve_update_bwd(Hc.data_ptr(), gc.data_ptr(), lc.data_ptr(), dl.data_ptr(), nb, K, C.byref(opts), R.data_ptr(), T.data_ptr(),
+                                        gR.data_ptr(), gT.data_ptr(), _ptr(gW), dH.data_ptr(), dg.data_ptr(), dlam.data_ptr(), dR.data_ptr(),
+                                        dT.data_ptr(), _ptr(dW), _stream()), "banet_lm_solve_update_bwd")
+    return dH, dg, dlam, dR, dT, dW
+
+
+def grad_fixed_concat_bwd(dconv2: Tensor, swap_halves: bool = False) -> Tensor:
+    lib = load()
+    g = _chk(dconv2, "dconv2"); nb, h, w, c3 = g.shape
+    dF = torch.empty(nb, h, w, c3 // 3, device=g.device)
+    check(lib.banet_grad_fixed_concat_bwd(g.data_ptr(), nb, h, w, c3 // 3, int(swap_halves), dF.data_ptr(), _stream()), "banet_grad_fixed_concat_bwd")
+    return dF
+
+
+def resample_bwd(dout: Tensor, xy: Tensor, coord_scale: float, h: int, w: int) -> Tensor:
+    lib = load()
+    g = _chk(dout, "dout"); nb, N, Cc = g.shape
+    pts = _chk(xy, "xy", (nb, N, 2))
+    dd = torch.empty(nb, h, w, Cc, device=g.device)
+    check(lib.banet_resample_bwd(g.data_ptr(), pts.data_ptr(), float(coord_scale), nb, h, w, Cc, N, dd.data_ptr(), _stream()), "banet_resample_bwd")
+    return dd
+
+
+def depth_compose_bwd(dout: Tensor, basis: Tensor, W: Tensor):
+    lib = load()
+    bs = _chk(basis, "basis"); nb, M, K = bs.shape
+    g = _chk(dout, "dout", (nb, M)); Wt = _chk(W, "W", (nb, K, 1))
+    dbasis = torch.empty_like(bs); dW = torch.empty(nb, K, 1, device=bs.device)
+    check(lib.banet_depth_compose_bwd(g.data_ptr(), bs.data_ptr(), Wt.data_ptr(), nb, M, K, dbasis.data_ptr(), dW.data_ptr(), _stream()), "banet_depth_compose_bwd")
+    return dbasis, dW

@@ -150,6 +150,41 @@ int    banet_lm_solve_update(const float* H, const float* g, const float* lambda
                              float* R_out, float* T_out, float* W_out, float* delta, int32_t* status,
                              void* ws, size_t ws_bytes, banet_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (3b) Backward of one LM iteration — the gradient signature of the reference's BA layer: TF autodiff of
+ *      bundlenet.py:193-278 with the registered op gradient EquationConstructionGrad (bundlenet.py:79-82,
+ *      utils.cu:465-694), w.r.t. every float input it differentiates: conv1, conv2, D, B, R, T, W (and, through
+ *      lambda, the MLP variables).  J, G, d and the tiled upstream gradients of utils.cu:613-617 are never formed.
+ * ---------------------------------------------------------------------------------------------- */
+/* Backward of banet_lm_build.  dH [nb,P,P] (as the solve's backward emits it: not symmetric), dg [nb,P],
+ * drbar_sum [nb,C]  ->  dconv1 [nb,N,C], dconv2 [nb,h,w,3C], dD [nb,N,1], dB [nb,N,K], dR [nb,3,3], dT [nb,3,1],
+ * dW [nb,K,1]; every output is overwritten.  conv2 must be the reference's [F2|gx|gy] layout (the F2-only layout
+ * adds banet_grad_fixed_concat_bwd).  exact_sym as in banet_eqc_bwd (0 = the reference's 2*A*Ghat). */
+int    banet_lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W,
+                          const float* dH, const float* dg, const float* drbar_sum, int exact_sym,
+                          float* dconv1, float* dconv2, float* dD, float* dB, float* dR, float* dT, float* dW,
+                          banet_stream_t stream);
+/* Backward of banet_lm_solve_update: gradients of (R',T',W') [dR_out,dT_out,dW_out] -> dH [nb,P,P], dg [nb,P],
+ * dlambda [nb], dR, dT, dW.  `delta` [nb,P] is the solution the forward call returned.  Pairs whose forward step was
+ * skipped (status != 0, delta = 0) pass the pose/depth gradients through and get zero dH, dg, dlambda.
+ * opts->vmatrix_batch_scramble must be 0. */
+int    banet_lm_solve_update_bwd(const float* H, const float* g, const float* lambda, const float* delta, int nb, int K,
+                                 const banet_solve_opts_t* opts, const float* R, const float* T,
+                                 const float* dR_out, const float* dT_out, const float* dW_out,
+                                 float* dH, float* dg, float* dlambda, float* dR, float* dT, float* dW,
+                                 banet_stream_t stream);
+/* Backward of banet_grad_fixed_concat (transposed REFLECT stencil + the half swap): dconv2 [nb,h,w,3C] -> dF [nb,h,w,C]. */
+int    banet_grad_fixed_concat_bwd(const float* dconv2, int nb, int h, int w, int C, int swap_halves,
+                                   float* dF, banet_stream_t stream);
+
+/* Backward of banet_resample w.r.t. the sampled map (the coordinates are constants on this path, bundlenet.py:343-344, 385):
+ *   dout [nb,N,C] -> ddata [nb,h,w,C] (overwritten). */
+int    banet_resample_bwd(const float* dout, const float* xy, float coord_scale, int nb, int h, int w, int C, int N,
+                          float* ddata, banet_stream_t stream);
+/* Backward of banet_depth_compose: dout [nb,M] -> dbasis [nb,M,K], dW [nb,K,1] (overwritten); d init_depth = dout. */
+int    banet_depth_compose_bwd(const float* dout, const float* basis, const float* W, int nb, int M, int K,
+                               float* dbasis, float* dW, banet_stream_t stream);
+
 /* Whole coarse-to-fine solve: for each level, `iters_per_level` iterations of
  * build -> lambda -> solve/update, with W carried across levels (the level loop of
  * bundlenet.py:376-399 with the iteration count of legacy/ba.py:106-121).
