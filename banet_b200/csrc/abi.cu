@@ -170,6 +170,18 @@ extern "C" int banet_lm_solve_update(const float* H, const float* g, const float
     return lm_solve_update(H, g, lambda, nb, K, *opts, R, T, W, R_out, T_out, W_out, delta, status, 0, (cudaStream_t)stream);
 }
 
+extern "C" int banet_lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K, const float* mlp_weights, float base,
+                             const float* lambda_in, const banet_solve_opts_t* opts, const float* R, const float* T, const float* W,
+                             float* R_out, float* T_out, float* W_out, float* delta, float* lambda_out, int32_t* status, banet_stream_t stream)
+{
+    BANET_REQUIRE(H && g && opts && R && T && R_out && T_out && delta && lambda_out && status && nb > 0 && K >= 0, BANET_ERR_BAD_ARG, "lm_step: bad argument");
+    BANET_REQUIRE((mlp_weights && rbar_sum && N > 0 && C > 0) || lambda_in, BANET_ERR_BAD_ARG, "lm_step: needs lambda-MLP weights + rbar_sum, or lambda_in");
+    BANET_REQUIRE(K == 0 || (W && W_out), BANET_ERR_BAD_ARG, "lm_step: K=%d but W is null", K);
+    BANET_REQUIRE(!opts->vmatrix_batch_scramble, BANET_ERR_UNSUPPORTED, "lm_step: vmatrix_batch_scramble needs the separate banet_lm_solve_update");
+    return lm_step(H, g, rbar_sum, nb, N, C > 0 ? C : 1, K, mlp_weights, base, lambda_in, *opts, R, T, W, R_out, T_out, W_out, delta, lambda_out, status, 0,
+                   (cudaStream_t)stream);
+}
+
 extern "C" int banet_lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W,
                                   const float* dH, const float* dg, const float* drbar_sum, int exact_sym,
                                   float* dconv1, float* dconv2, float* dD, float* dB, float* dR, float* dT, float* dW, banet_stream_t stream)
@@ -270,6 +282,13 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
         for (int it = 0; it < iters_per_level; ++it) {
             rc = build_dispatch(lv, res, plan, R, T, W, H, g, rbar, nvalid, base + c.build, st);
             if (rc) return rc;
+            const int P = 6 + K;
+            if (!opts->vmatrix_batch_scramble && lm_step_supported(P, lv->C)) {      // one launch: lambda-MLP + damping + Cholesky + update
+                rc = lm_step(H, g, rbar, nb, lv->N, lv->C, K, use_mlp ? mlp_weights[l] : nullptr, l2_regularizer_base, lam, *opts,
+                             R, T, W, R, T, W, delta, lam, status, 1, st);
+                if (rc) return rc;
+                continue;
+            }
             if (use_mlp) {
                 rc = lm_lambda(rbar, nb, lv->N, lv->C, mlp_weights[l], l2_regularizer_base, lam, st);
                 if (rc) return rc;

@@ -53,6 +53,12 @@ int lm_solve_update(const float* H, const float* g, const float* lambda, int nb,
                     const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
                     float* delta, int32_t* status, int status_accumulate, cudaStream_t st);
 
+// fused lambda-MLP + damping + blocked Cholesky + update, one launch (lm_step.cu); mlp == nullptr: lambda_in is used as is
+bool lm_step_supported(int P, int C);
+int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K, const float* mlp, float base, const float* lambda_in,
+            const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+            float* delta, float* lambda_out, int32_t* status, int status_accumulate, cudaStream_t st);
+
 // backward of one iteration (lm_bwd.cu)
 int lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W, const float* dH, const float* dg, const float* drbar,
                  int exact_sym, float* dconv1, float* dconv2, float* dD, float* dB, float* dR, float* dT, float* dW, cudaStream_t st);

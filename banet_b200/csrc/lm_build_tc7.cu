@@ -89,7 +89,6 @@ __device__ __forceinline__ float qsum8(float v) {               // sum over the 
     v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
 }
-#define TC6_TRACE(role, it, slot) do { } while (0)
 struct TileCoord { int b, n0, cnt, tx0, ty0; };
 // tile index -> (pair, 8x8 patch): bands of prm.band_rows tile rows, column by column inside a band
 __device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long long tl) {
@@ -522,9 +521,14 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             const bool last_of_pair = (++rr == prm.tiles_per_pair) || (j == ntiles - 1);
             if (rr == prm.tiles_per_pair) rr = 0;
             const unsigned char* As = base + SM::off_A + s * STAGE_A;
-            if (awi == 0) TC6_TRACE(1, j, 0);
+            if (j > 0) {
+                // MMAs of tile j-1 done: R / A_lo and stage (j-1) % NST are free.  Refill the stage BEFORE waiting for the gather of tile j: the
+                // window producer (gather warp 0) looks ahead into tile j+1 and waits for its records, i.e. for the geometry warps, i.e. for
+                // this very TMA when NST == 2 -- issued after gath[j] it would close a cycle through the gather warps themselves.
+                mbar_wait_parked(rfree, (j - 1) & 1);
+                if (awi == 0 && lane == 0 && j - 1 + NST < ntiles) issue_tma(j - 1 + NST);
+            }
             mbar_wait_parked(&gath[sr], (j / NREC) & 1);
-            if (awi == 0) TC6_TRACE(1, j, 1);
             const int b = sTile[sr * 4];
             if (b != scale_b) { scale_b = b; ++sspan; fx = __ldg(prm.intr + b * 4); fy = __ldg(prm.intr + b * 4 + 1); }
             float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -559,13 +563,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&recfree[sr]);        // the record buffer may be refilled (everything needed is in registers)
             const float sn = __shfl_sync(0xffffffffu, ext[7], r16);   // s_n of this lane's row
-            if (awi == 0) TC6_TRACE(1, j, 2);
             mbar_wait_parked(&fullB[s], (j / NST) & 1);      // long complete; orders the TMA writes before the reads below
-            if (j > 0) {
-                mbar_wait_parked(rfree, (j - 1) & 1);        // MMAs of tile j-1 done: R / A_lo / R_lo and stage (j-1) % NST are free
-                if (awi == 0 && lane == 0 && j - 1 + NST < ntiles) issue_tma(j - 1 + NST);
-            }
-            if (awi == 0) TC6_TRACE(1, j, 3);
             if (lane < 16) {                                 // R columns 128..134 = [v(6) | t], column 135 stays zero
                 const float4 e0 = make_float4(tf32_rna(ext[0]), tf32_rna(ext[1]), tf32_rna(ext[2]), tf32_rna(ext[3]));
                 const float4 e1 = make_float4(tf32_rna(ext[4]), tf32_rna(ext[5]), tf32_rna(ext[6]), 0.f);
@@ -595,7 +593,6 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                     *reinterpret_cast<float4*>(base + SM::off_Rlo + off) = make_float4(pv.x - hv.x, pv.y - hv.y, pv.z - hv.z, pv.w - hv.w);
             }
             fence_proxy_async_smem();
-            if (awi == 0) TC6_TRACE(1, j, 4);
             team_bar<AW * 32>();                           // all 64 rows written
             if (awi == 0) {
                 if (lane == 0) {                             // ---- tcgen05.mma issue for this tile
@@ -622,7 +619,6 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                 }
                 __syncwarp();
             }
-            if (awi == 0) TC6_TRACE(1, j, 5);
             if (last_of_pair) flush(sspan);
         }
     } else {

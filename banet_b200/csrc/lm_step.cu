@@ -1,0 +1,284 @@
+// One kernel for everything of an LM iteration that is not the normal-equation build: lambda-MLP, damping, blocked Cholesky with the
+// right-hand side carried as an extra row, blocked back substitution, SE(3) / depth-coefficient update.
+//
+// Replaces, per iteration, lm_lambda_kernel + lm_solve_kernel + pose_update_kernel (lm_solve.cu; reference bundlenet.py:241-253, 264-276):
+// those are three launches of nb CTAs whose run time is pure dependent latency (measured round 1: 64 + 215..258 + 5 us, about 11 % of a cfg2
+// solve).  Here: one launch, one CTA (1024 threads) per pair:
+//   1. rbar = rbar_sum / N, ||rbar||; 5 dense layers C->2C->4C->2C->C->1 (selu x4, tanh): warps take (32 outputs x an input slice) tasks,
+//      lanes over consecutive outputs (coalesced 128-B weight rows, 8 rows in flight per lane), slices combined through shared memory;
+//      lambda = base * ||rbar||^(2 + tanh(.))                                                            (bundlenet.py:243-253)
+//   2. packed lower triangle of H (+ damping on the diagonal) and g as row P of the same packed array, in S = double (P <= 200) or float;
+//   3. right-looking Cholesky in panels of 8 columns: thread 0 factors the 8x8 diagonal block, one thread per row solves the panel rows
+//      (row P = the right-hand side: forward substitution comes for free), warp-per-row trailing update: 3 block barriers per panel instead
+//      of one per column;
+//   4. back substitution L^T x = y panel by panel (8 warps form the 8 dot products of a panel, thread 0 solves the 8x8 triangle);
+//   5. delta, W' = W + delta_d, status; R' = exp(w) R, T' = V(w) t + exp(w) T in double by thread 0 (per-pair VMatrix).
+// The reference's batch-interleaved VMatrix (vmatrix_batch_scramble, bundlenet.py:45) needs every pair's delta first: the host falls back to
+// the three-kernel path for that option.
+#include "common.cuh"
+#include "lm_build.h"
+
+namespace banet {
+
+constexpr int STEP_THREADS = 1024;
+constexpr int STEP_WARPS = STEP_THREADS / 32;
+constexpr int STEP_NB = 8;                       // Cholesky panel width
+
+__device__ __forceinline__ float selu_s(float x) {
+    const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+    return scale * (x > 0.f ? x : alpha * expm1f(x));
+}
+__host__ __device__ __forceinline__ int tri3(int i, int k) { return i * (i + 1) / 2 + k; }
+
+// one dense layer: out[j] = act(bias[j] + sum_i in[i] W[i][j]);  W row-major [cin][cout].  Tasks = (32-output block) x (input slice); partial
+// sums meet in `acc` (shared, zeroed by the caller) through shared-memory atomics; one barrier later the activation is applied.
+__device__ __forceinline__ void dense_layer(const float* __restrict__ in, const float* __restrict__ Wm, const float* __restrict__ bias,
+                                            int cin, int cout, bool last, float* __restrict__ acc, float* __restrict__ out, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    const int jblocks = (cout + 31) / 32;
+    int slices = STEP_WARPS / jblocks; if (slices < 1) slices = 1; if (slices > cin / 8) slices = max(1, cin / 8);
+    const int ntask = jblocks * slices;
+    const int rows = (cin + slices - 1) / slices;
+    for (int t = warp; t < ntask; t += STEP_WARPS) {
+        const int jb = t % jblocks, sl = t / jblocks;
+        const int j = jb * 32 + lane, i0 = sl * rows, i1 = min(cin, i0 + rows);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (j < cout) {
+            int i = i0;
+            for (; i + 7 < i1; i += 8) {
+                const float w0 = __ldg(Wm + (size_t)i * cout + j), w1 = __ldg(Wm + (size_t)(i + 1) * cout + j), w2 = __ldg(Wm + (size_t)(i + 2) * cout + j),
+                            w3 = __ldg(Wm + (size_t)(i + 3) * cout + j), w4 = __ldg(Wm + (size_t)(i + 4) * cout + j), w5 = __ldg(Wm + (size_t)(i + 5) * cout + j),
+                            w6 = __ldg(Wm + (size_t)(i + 6) * cout + j), w7 = __ldg(Wm + (size_t)(i + 7) * cout + j);
+                a0 = fmaf(in[i], w0, a0); a1 = fmaf(in[i + 1], w1, a1); a2 = fmaf(in[i + 2], w2, a2); a3 = fmaf(in[i + 3], w3, a3);
+                a0 = fmaf(in[i + 4], w4, a0); a1 = fmaf(in[i + 5], w5, a1); a2 = fmaf(in[i + 6], w6, a2); a3 = fmaf(in[i + 7], w7, a3);
+            }
+            for (; i < i1; ++i) a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
+            atomicAdd(&acc[j], (a0 + a1) + (a2 + a3));
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < cout; j += STEP_THREADS) {
+        const float z = acc[j] + __ldg(bias + j);
+        out[j] = last ? tanhf(z) : selu_s(z);
+    }
+    __syncthreads();
+}
+
+template <typename S>
+__global__ void __launch_bounds__(STEP_THREADS)
+lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const float* __restrict__ rbar_sum, int N, int C,
+               const float* __restrict__ mlp, float base, const float* __restrict__ lambda_in, int P, float eps, int ndamped,
+               const float* __restrict__ R, const float* __restrict__ T, const float* __restrict__ W,
+               float* __restrict__ R_out, float* __restrict__ T_out, float* __restrict__ W_out,
+               float* __restrict__ delta, float* __restrict__ lambda_out, int32_t* __restrict__ status, int status_accumulate)
+{
+    extern __shared__ __align__(16) unsigned char smraw[];
+    S* A = reinterpret_cast<S*>(smraw);                              // packed lower triangle, rows 0..P (row P = right-hand side)
+    const size_t nA = (size_t)(P + 1) * (P + 2) / 2;
+    S* xs = A + nA;                                                  // [P] solution
+    S* dots = xs + P;                                                // [STEP_NB]
+    float* mbuf = reinterpret_cast<float*>(dots + STEP_NB);          // MLP buffers: 3 x 4C floats
+    __shared__ int s_flag;
+    __shared__ float s_norm2, s_lam;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = P - 6;
+    if (tid == 0) { s_flag = 0; s_norm2 = 0.f; }
+    __syncthreads();
+
+    // ---- 1. lambda -------------------------------------------------------------------------------------------------------------------
+    float lam;
+    if (mlp) {
+        float* bufA = mbuf; float* bufB = mbuf + 4 * C; float* acc = mbuf + 8 * C;
+        const float invN = 1.0f / (float)N;
+        float part = 0.f;
+        for (int c = tid; c < C; c += STEP_THREADS) { const float r = rbar_sum[(size_t)b * C + c] * invN; bufA[c] = r; part += r * r; }
+        for (int c = tid; c < 4 * C; c += STEP_THREADS) acc[c] = 0.f;
+        part = warp_sum(part);
+        if (lane == 0 && part != 0.f) atomicAdd(&s_norm2, part);
+        __syncthreads();
+        const int dims[6] = {C, 2 * C, 4 * C, 2 * C, C, 1};
+        const float* wp = mlp;
+        float* in = bufA; float* out = bufB;
+        for (int l = 0; l < 5; ++l) {
+            const int cin = dims[l], cout = dims[l + 1];
+            dense_layer(in, wp, wp + (size_t)cin * cout, cin, cout, l == 4, acc, out, tid);
+            for (int c = tid; c < cout; c += STEP_THREADS) acc[c] = 0.f;       // ready for the next layer (visible after its first barrier)
+            wp += (size_t)cin * cout + cout;
+            float* tmp = in; in = out; out = tmp;
+            __syncthreads();
+        }
+        if (tid == 0) { s_lam = base * powf(sqrtf(s_norm2), 2.0f + in[0]); lambda_out[b] = s_lam; }   // bundlenet.py:249,253
+        __syncthreads();
+        lam = s_lam;
+    } else {
+        lam = lambda_in[b];
+        if (tid == 0) lambda_out[b] = lam;
+    }
+
+    // ---- 2. load (+ damping, bundlenet.py:264-266 / :181-182) -------------------------------------------------------------------------------
+    const float* Hb = H + (size_t)b * P * P;
+    int bad = 0;
+    for (int i = warp; i < P; i += STEP_WARPS)
+        for (int k = lane; k <= i; k += 32) {
+            const float v = Hb[(size_t)i * P + k];
+            if (!isfinite(v)) bad = 1;
+            S sv = (S)v;
+            if (k == i && i < ndamped) sv += ((S)v + (S)eps) * (S)lam;
+            A[tri3(i, k)] = sv;
+        }
+    for (int k = tid; k < P; k += STEP_THREADS) { const float v = g[(size_t)b * P + k]; if (!isfinite(v)) bad = 1; A[tri3(P, k)] = (S)v; }
+    if (!isfinite(lam)) bad = 1;
+    if (bad) atomicOr(&s_flag, 2);
+    __syncthreads();
+
+    // ---- 3. blocked Cholesky; row P rides along: afterwards A[P][:] = y = L^-1 g ----------------------------------------------------------------
+    for (int j0 = 0; j0 < P; j0 += STEP_NB) {
+        const int jb = min(STEP_NB, P - j0);
+        if (tid == 0) {                                              // 8x8 diagonal block, in place
+            for (int c = 0; c < jb; ++c) {
+                S d = A[tri3(j0 + c, j0 + c)];
+                for (int m = 0; m < c; ++m) { const S l = A[tri3(j0 + c, j0 + m)]; d -= l * l; }
+                if (!(d > (S)0)) { s_flag |= 1; d = (S)1; }
+                const S ld = sqrt(d);
+                A[tri3(j0 + c, j0 + c)] = ld;
+                const S inv = (S)1 / ld;
+                for (int r = c + 1; r < jb; ++r) {
+                    S v = A[tri3(j0 + r, j0 + c)];
+                    for (int m = 0; m < c; ++m) v -= A[tri3(j0 + r, j0 + m)] * A[tri3(j0 + c, j0 + m)];
+                    A[tri3(j0 + r, j0 + c)] = v * inv;
+                }
+            }
+        }
+        __syncthreads();
+        {                                                            // panel rows: L21[i][:] = A21[i][:] L11^-T, one thread per row (incl. row P)
+            const int i = j0 + jb + tid;
+            if (i <= P) {
+                S row[STEP_NB];
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) row[c] = (c < jb) ? A[tri3(i, j0 + c)] : (S)0;
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) {
+                    if (c < jb) {
+                        S v = row[c];
+#pragma unroll
+                        for (int m = 0; m < STEP_NB; ++m) if (m < c) v -= row[m] * A[tri3(j0 + c, j0 + m)];
+                        row[c] = v / A[tri3(j0 + c, j0 + c)];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) if (c < jb) A[tri3(i, j0 + c)] = row[c];
+            }
+        }
+        __syncthreads();
+        for (int i = j0 + jb + warp; i <= P; i += STEP_WARPS) {      // trailing update, warp per row, lanes over columns
+            S li[STEP_NB];
+#pragma unroll
+            for (int c = 0; c < STEP_NB; ++c) li[c] = (c < jb) ? A[tri3(i, j0 + c)] : (S)0;
+            const int kend = (i == P) ? P - 1 : i;
+            for (int k = j0 + jb + lane; k <= kend; k += 32) {
+                S s = (S)0;
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) if (c < jb) s += li[c] * A[tri3(k, j0 + c)];
+                A[tri3(i, k)] -= s;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 4. back substitution L^T x = y, panels from the bottom ----------------------------------------------------------------------------
+    const int npan = (P + STEP_NB - 1) / STEP_NB;
+    for (int pnl = npan - 1; pnl >= 0; --pnl) {
+        const int j0 = pnl * STEP_NB, jb = min(STEP_NB, P - j0);
+        if (warp < jb) {                                             // dots[c] = sum_{i >= j0+jb} L[i][j0+c] x[i]
+            S s = (S)0;
+            for (int i = j0 + jb + lane; i < P; i += 32) s += A[tri3(i, j0 + warp)] * xs[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) dots[warp] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int c = jb - 1; c >= 0; --c) {
+                S v = A[tri3(P, j0 + c)] - dots[c];
+                for (int m = c + 1; m < jb; ++m) v -= A[tri3(j0 + m, j0 + c)] * xs[j0 + m];
+                xs[j0 + c] = v / A[tri3(j0 + c, j0 + c)];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- 5. outputs ----------------------------------------------------------------------------------------------------------------------------
+    const int flag = s_flag;
+    for (int i = tid; i < P; i += STEP_THREADS) {
+        float dv = flag ? 0.f : (float)xs[i];
+        if (!isfinite(dv)) dv = 0.f;
+        delta[(size_t)b * P + i] = dv;
+        if (i >= 6) W_out[(size_t)b * K + i - 6] = W[(size_t)b * K + i - 6] + dv;      // bundlenet.py:276
+    }
+    if (tid == 0) {
+        status[b] = status_accumulate ? (status[b] | flag) : flag;
+        double dl[6];
+        for (int i = 0; i < 6; ++i) { float dv = flag ? 0.f : (float)xs[i]; if (!isfinite(dv)) dv = 0.f; dl[i] = (double)dv; }
+        const double wx = dl[0], wy = dl[1], wz = dl[2], tx = dl[3], ty = dl[4], tz = dl[5];
+        const double th_raw = sqrt(wx * wx + wy * wy + wz * wz);
+        const double th = fmax(th_raw, 1e-6);                        // AngleaAxisRotation (bundlenet.py:17-37)
+        const double kx = wx / th, ky = wy / th, kz = wz / th, c = cos(th), s = sin(th), oc = 1.0 - c;
+        const double dr[9] = {c + kx * kx * oc,      kx * ky * oc - kz * s, ky * s + kx * kz * oc,
+                              kz * s + kx * ky * oc, c + ky * ky * oc,      -kx * s + ky * kz * oc,
+                              -ky * s + kx * kz * oc, kx * s + ky * kz * oc, c + kz * kz * oc};
+        double ca, cb;                                               // VMatrix (bundlenet.py:39-46), series below 1e-4
+        if (th_raw < 1e-4) { ca = 0.5 - th_raw * th_raw / 24.0; cb = 1.0 / 6.0 - th_raw * th_raw / 120.0; }
+        else { ca = (1.0 - cos(th_raw)) / (th_raw * th_raw); cb = (th_raw - sin(th_raw)) / (th_raw * th_raw * th_raw); }
+        const double sk[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+        double V[9];
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+            const double sk2 = sk[i * 3] * sk[j] + sk[i * 3 + 1] * sk[3 + j] + sk[i * 3 + 2] * sk[6 + j];
+            V[i * 3 + j] = ((i == j) ? 1.0 : 0.0) + ca * sk[i * 3 + j] + cb * sk2;
+        }
+        double Rin[9], Tin[3];
+        for (int q = 0; q < 9; ++q) Rin[q] = R[(size_t)b * 9 + q];
+        for (int q = 0; q < 3; ++q) Tin[q] = T[(size_t)b * 3 + q];
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j)
+                R_out[(size_t)b * 9 + i * 3 + j] = (float)(dr[i * 3] * Rin[j] + dr[i * 3 + 1] * Rin[3 + j] + dr[i * 3 + 2] * Rin[6 + j]);
+            T_out[(size_t)b * 3 + i] = (float)(V[i * 3] * tx + V[i * 3 + 1] * ty + V[i * 3 + 2] * tz
+                                               + dr[i * 3] * Tin[0] + dr[i * 3 + 1] * Tin[1] + dr[i * 3 + 2] * Tin[2]);
+        }
+    }
+}
+
+size_t lm_step_smem(int P, int C, bool use_double)
+{
+    const size_t nA = (size_t)(P + 1) * (P + 2) / 2 + P + STEP_NB;
+    return nA * (use_double ? sizeof(double) : sizeof(float)) + (size_t)12 * C * sizeof(float);
+}
+
+bool lm_step_supported(int P, int C) { return lm_step_smem(P, C, false) <= 220 * 1024; }
+
+// mlp == nullptr: lambda_in [nb] is used as is.  In-place R/T/W (R_out == R ...) is fine: a pair's CTA reads before it writes.
+int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K, const float* mlp, float base, const float* lambda_in,
+            const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+            float* delta, float* lambda_out, int32_t* status, int status_accumulate, cudaStream_t st)
+{
+    const int P = 6 + K;
+    const int ndamped = opts.undamped_last ? P - 1 : P;
+    const bool use_double = lm_step_smem(P, C, true) <= 200 * 1024;
+    const size_t smem = lm_step_smem(P, C, use_double);
+    BANET_REQUIRE(smem <= 220 * 1024, BANET_ERR_UNSUPPORTED, "lm_step: P=%d, C=%d do not fit shared memory", P, C);
+    cudaError_t e;
+    if (use_double) {
+        e = cudaFuncSetAttribute(lm_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
+        lm_step_kernel<double><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, P, opts.damping_eps, ndamped, R, T, W,
+                                                               R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
+    } else {
+        e = cudaFuncSetAttribute(lm_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
+        lm_step_kernel<float><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, P, opts.damping_eps, ndamped, R, T, W,
+                                                              R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
+    }
+    BANET_CUDA_LAUNCH_CHECK("lm_step_kernel launch");
+    return BANET_OK;
+}
+
+}  // namespace banet

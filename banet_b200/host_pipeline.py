@@ -101,3 +101,99 @@ class HostSolver:
         for t_ in (R, T, W, status, dR, dT, dW):
             t_.record_stream(self.compute_stream)
         return R, T, W, status
+
+
+class ResizeHostSolver:
+    """The reference's `BundleResize` boundary (bundlenet.py:332-399) with HOST inputs, for dense pyramid levels: a batch of `nimg` images
+    comes in as feature maps `layers[l]` [nimg,h_l,w_l,C] (coarse -> fine), half-resolution `basis` [nimg,H/2,W/2,K] and `init_depth`
+    [nimg,H/2,W/2,1] and finest-level intrinsics `intr` [nimg,4]; pair b = (image b, image (b + nimg/2) % nimg) (:386).  Everything the
+    reference derives in its graph is derived on the device, nothing derivable crosses PCIe:
+        conv1 = layers[l] itself (the points are the level's own pixel grid, so resampler(layers[l], points) is the identity: zero copy);
+        conv2 = the other half of the same buffer, F2 only (gradients on the fly in the build kernel, bundlenet.py:92-100, 386-389);
+        p = computeCoordinates(points_l, intr / scale_l) (:358);  D, B = resampler(init_depth | basis, points / 2) (:343-344).
+    Pairs are cut into chunks inside each half of the batch; the H2D copies of the images a later chunk needs overlap the solve of the
+    current one (copy stream / compute stream)."""
+
+    def __init__(self, layers: Sequence[Tensor], basis: Tensor, init_depth: Tensor, intr: Tensor, scales: Sequence[int], chunks: int = 4,
+                 device=None, precision: int = PREC_AUTO):
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.h_layers = list(layers); self.h_basis = basis; self.h_depth = init_depth; self.h_intr = intr
+        self.scales = [int(s) for s in scales]
+        self.precision = precision
+        self.nimg = int(basis.shape[0]); self.half = self.nimg // 2
+        if self.nimg % 2:
+            raise ValueError("the half-swap pairing of bundlenet.py:386 needs an even batch")
+        per_half = max(1, int(chunks) // 2)
+        self.ranges = [(o + a, o + b) for o in (0, self.half) for a, b in chunk_ranges(self.half, per_half)]
+        self.copy_stream = torch.cuda.Stream(self.dev); self.compute_stream = torch.cuda.Stream(self.dev)
+        dev = self.dev
+        self.d_layers = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in self.h_layers]
+        self.d_basis = torch.empty(basis.shape, dtype=torch.float32, device=dev)
+        self.d_depth = torch.empty(init_depth.shape, dtype=torch.float32, device=dev)
+        self.d_intr = torch.empty(intr.shape, dtype=torch.float32, device=dev)
+        self.h2d_bytes = 4 * (sum(t.numel() for t in self.h_layers) + basis.numel() + init_depth.numel() + intr.numel())
+        self.K = int(basis.shape[-1]); self.C = int(self.h_layers[0].shape[-1])
+        nmax = max(b - a for a, b in self.ranges)
+        self.pts, self.scr = [], []
+        for t, s in zip(self.h_layers, self.scales):                      # per level: dense pixel grid + scratch for the derived tensors of one chunk
+            h, w = int(t.shape[1]), int(t.shape[2]); N = h * w
+            vv, uu = torch.meshgrid(torch.arange(h, device=dev, dtype=torch.float32), torch.arange(w, device=dev, dtype=torch.float32), indexing="ij")
+            self.pts.append(torch.stack([uu.reshape(-1), vv.reshape(-1)], -1).unsqueeze(0).repeat(nmax, 1, 1).contiguous())
+            self.scr.append({"B": torch.empty(nmax, N, self.K, device=dev), "D": torch.empty(nmax, N, 1, device=dev), "p": torch.empty(nmax, 3, N, device=dev)})
+        self._ws: Optional[Tensor] = None
+
+    def _chunk_levels(self, a: int, b: int) -> List[ops.Level]:
+        n = b - a
+        a2 = (a + self.half) % self.nimg
+        lib = ops.load()
+        levels = []
+        for l, (dl, s) in enumerate(zip(self.d_layers, self.scales)):
+            h, w = int(dl.shape[1]), int(dl.shape[2]); N = h * w
+            pts = self.pts[l][:n]; scr = self.scr[l]
+            intr_l = (self.d_intr[a:b] / float(s)).contiguous()
+            ops.check(lib.banet_compute_coordinates(pts.data_ptr(), intr_l.data_ptr(), n, N, 1, scr["p"].data_ptr(), ops._stream()), "banet_compute_coordinates")
+            ops.check(lib.banet_resample(self.d_depth[a:b].data_ptr(), pts.data_ptr(), s / 2.0, n, int(self.d_depth.shape[1]), int(self.d_depth.shape[2]), 1, N,
+                                         scr["D"].data_ptr(), ops._stream()), "banet_resample")
+            ops.check(lib.banet_resample(self.d_basis[a:b].data_ptr(), pts.data_ptr(), s / 2.0, n, int(self.d_basis.shape[1]), int(self.d_basis.shape[2]), self.K, N,
+                                         scr["B"].data_ptr(), ops._stream()), "banet_resample")
+            levels.append(ops.Level(dl[a:b].reshape(n, N, self.C), dl[a2:a2 + n], intr_l, scr["p"][:n], scr["D"][:n], scr["B"][:n], grid=(w, h)))
+        return levels
+
+    def solve(self, R0: Tensor, T0: Tensor, W0: Tensor, iters_per_level: int, mlp_packed=None, l2_regularizer_base: float = 1000.0,
+              lambda_fixed: float = -1.0, out: Optional[Tuple[Tensor, Tensor, Tensor]] = None):
+        """R0 [nimg,3,3], T0 [nimg,3,1], W0 [nimg,K,1] on the host.  Returns device (R, T, W, status); `out` = three host tensors receive them too."""
+        nimg, dev = self.nimg, self.dev
+        R = torch.empty(nimg, 3, 3, device=dev); T = torch.empty(nimg, 3, 1, device=dev); W = torch.empty(W0.shape, device=dev)
+        status = torch.empty(nimg, dtype=torch.int32, device=dev)
+        dR = torch.empty_like(R); dT = torch.empty_like(T); dW = torch.empty_like(W)
+        cur = torch.cuda.current_stream(dev)
+        self.copy_stream.wait_stream(cur); self.compute_stream.wait_stream(cur)
+        events, resident = [], set()
+        with torch.cuda.stream(self.copy_stream):
+            self.d_intr.copy_(self.h_intr, non_blocking=True)
+            for a, b in self.ranges:
+                a2 = (a + self.half) % nimg
+                for lo, hi in ((a, b), (a2, a2 + (b - a))):                  # images this chunk reads (frame 1, frame 2) that are not on the device yet
+                    if (lo, hi) in resident:
+                        continue
+                    resident.add((lo, hi))
+                    for dl, hl in zip(self.d_layers, self.h_layers):
+                        dl[lo:hi].copy_(hl[lo:hi], non_blocking=True)
+                self.d_basis[a:b].copy_(self.h_basis[a:b], non_blocking=True); self.d_depth[a:b].copy_(self.h_depth[a:b], non_blocking=True)
+                dR[a:b].copy_(R0[a:b], non_blocking=True); dT[a:b].copy_(T0[a:b], non_blocking=True); dW[a:b].copy_(W0[a:b], non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(self.copy_stream); events.append(ev)
+        with torch.cuda.stream(self.compute_stream):
+            for (a, b), ev in zip(self.ranges, events):
+                self.compute_stream.wait_event(ev)
+                lv = self._chunk_levels(a, b)
+                if self._ws is None:
+                    self._ws = torch.empty(ops.lm_run_workspace_bytes(lv, self.precision), dtype=torch.uint8, device=dev)
+                r, t, w, st = ops.lm_run(lv, iters_per_level, dR[a:b], dT[a:b], dW[a:b], mlp_packed=mlp_packed, l2_regularizer_base=l2_regularizer_base,
+                                         lambda_fixed=lambda_fixed, workspace=self._ws, precision=self.precision)
+                R[a:b] = r; T[a:b] = t; W[a:b] = w; status[a:b] = st
+                if out is not None:
+                    out[0][a:b].copy_(r, non_blocking=True); out[1][a:b].copy_(t, non_blocking=True); out[2][a:b].copy_(w, non_blocking=True)
+        cur.wait_stream(self.compute_stream)
+        for t_ in (R, T, W, status, dR, dT, dW):
+            t_.record_stream(self.compute_stream)
+        return R, T, W, status

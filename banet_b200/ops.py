@@ -222,6 +222,29 @@ def lm_solve_update(H: Tensor, g: Tensor, lam: Tensor, R: Tensor, T: Tensor, W: 
     return Ro, To, Wo, delta, status
 
 
+def lm_step(H: Tensor, g: Tensor, rbar_sum: Optional[Tensor], N: int, mlp_packed: Optional[Tensor], base: float, R: Tensor, T: Tensor,
+            W: Optional[Tensor], lam: Optional[Tensor] = None, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None):
+    """banet_lm_step: lambda-MLP (or the given `lam`) + damping + solve + update in one launch -> R', T', W', delta, lambda, status."""
+    lib = load()
+    Hc = _chk(H, "H"); nb, P, _ = Hc.shape
+    K = P - 6
+    gc = _chk(g.reshape(nb, P), "g", (nb, P))
+    R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1)); Wt = None if K == 0 else _chk(W, "W", (nb, K, 1))
+    rb = None if rbar_sum is None else _chk(rbar_sum, "rbar_sum"); mp = None if mlp_packed is None else _chk(mlp_packed, "mlp_packed")
+    lin = None if lam is None else _chk(lam.reshape(nb), "lambda", (nb,))
+    Cc = 1 if rb is None else rb.shape[1]
+    if undamped_last is None:
+        undamped_last = K > 0
+    dev = Hc.device
+    Ro = torch.empty_like(R); To = torch.empty_like(T); Wo = None if K == 0 else torch.empty_like(Wt)
+    delta = torch.empty(nb, P, device=dev); lout = torch.empty(nb, device=dev); status = torch.empty(nb, device=dev, dtype=torch.int32)
+    opts = BanetSolveOpts(float(damping_eps), int(undamped_last), 0)
+    check(lib.banet_lm_step(Hc.data_ptr(), gc.data_ptr(), _ptr(rb), nb, int(N), Cc, K, _ptr(mp), float(base), _ptr(lin), C.byref(opts), R.data_ptr(),
+                            T.data_ptr(), _ptr(Wt), Ro.data_ptr(), To.data_ptr(), _ptr(Wo), delta.data_ptr(), lout.data_ptr(), status.data_ptr(), _stream()),
+          "banet_lm_step")
+    return Ro, To, Wo, delta, lout, status
+
+
 def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
            mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: float = 1000.0,
            lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,

@@ -181,3 +181,76 @@ def make_scene(nb: int, H: int, W: int, C: int, K: int, level_ids=(0, 1, 2, 3), 
             conv1[b0:b1] = bilinear_zero_pad(f2, px, py)
         levels.append(SceneLevel(lid, h, w, conv1, conv2, intr, p.contiguous(), D, Bm, pts, (w, h) if n_points is None else None))
     return Scene(levels, R_true, T_true, W_true, R0, T0, W0)
+
+
+@dataclass
+class ResizeScene:
+    """Inputs at the layer boundary of the reference's BundleResize (bundlenet.py:332-399) for dense pyramid levels: a batch of `nimg` images,
+    pair b = (image b, image (b + nimg/2) % nimg) (the half swap of :386)."""
+    layers: List[torch.Tensor]          # per level (coarse -> fine) [nimg,h_l,w_l,C] feature maps of every image
+    basis: torch.Tensor                 # [nimg,H/2,W/2,K] depth basis of every image (as frame 1 of its pair)
+    init_depth: torch.Tensor            # [nimg,H/2,W/2,1]
+    intr: torch.Tensor                  # [nimg,4] fx,fy,ox,oy at the finest level
+    scales: List[int]                   # per level: finest-level pixels per level pixel
+    R0: torch.Tensor; T0: torch.Tensor; W0: torch.Tensor
+
+
+def make_resize_scene(nimg: int, H: int, W: int, C: int, K: int, level_ids=(0, 1, 2, 3), seed: int = 1234, device="cpu", dtype=torch.float32,
+                      rot_deg: float = 1.0, trans_m: float = 0.02, w_std: float = 0.02, start_trans_noise_m: float = 0.01, pair_chunk: int = 4) -> ResizeScene:
+    """Planted-solution batch for the BundleResize boundary.  For the first nimg/2 pairs (b, b + nimg/2) the features of image b at every
+    level are the features of image b + nimg/2 sampled at the warp of the level's pixel grid under a planted (R*, T*, D + B.W*), with D and B
+    resampled from the half-resolution depth / basis maps exactly as the solver derives them; the second half of the pairs are the same
+    image pairs in the opposite direction (a genuine, non-zero-residual LM problem)."""
+    assert nimg % 2 == 0
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    dev = torch.device(device)
+    half = nimg // 2
+
+    def randn(*s_):
+        return torch.randn(*s_, generator=g, dtype=torch.float32).to(dev, dtype)
+
+    def rand(*s_):
+        return torch.rand(*s_, generator=g, dtype=torch.float32).to(dev, dtype)
+
+    hb, wb = H // 2, W // 2
+    intr = torch.tensor(TUM_INTRINSICS, device=dev, dtype=dtype).mul(W / 640.0).unsqueeze(0).repeat(nimg, 1)
+    basis = torch.empty(nimg, hb, wb, K, device=dev, dtype=dtype)
+    depth = torch.empty(nimg, hb, wb, 1, device=dev, dtype=dtype)
+    for b0 in range(0, nimg, pair_chunk):
+        b1 = min(nimg, b0 + pair_chunk); n = b1 - b0
+        bm = gaussian_blur_nchw(randn(n, K, hb, wb), 4.0)
+        basis[b0:b1] = (bm * torch.rsqrt(bm.flatten(2).var(dim=2) + 1e-3).view(n, K, 1, 1)).permute(0, 2, 3, 1)
+        dm = gaussian_blur_nchw(1.0 + 2.0 * rand(n, 1, hb, wb), 4.0).permute(0, 2, 3, 1)
+        dmin = dm.flatten(1).min(1).values.view(n, 1, 1, 1); dmax = dm.flatten(1).max(1).values.view(n, 1, 1, 1)
+        depth[b0:b1] = 1.0 + 2.0 * (dm - dmin) / (dmax - dmin).clamp_min(1e-6)
+    w_true = randn(half, 3) * math.radians(rot_deg)
+    R_true = rodrigues(w_true); T_true = (randn(half, 3) * trans_m).unsqueeze(-1); W_true = (randn(half, K) * w_std).unsqueeze(-1)
+    layers, scales = [], []
+    for lid in level_ids:
+        s_ = 2 ** (3 - lid); scales.append(s_)
+        h, w = H // s_, W // s_
+        feat = torch.empty(nimg, h, w, C, device=dev, dtype=dtype)
+        li = intr / s_
+        vv, uu = torch.meshgrid(torch.arange(h, device=dev, dtype=dtype), torch.arange(w, device=dev, dtype=dtype), indexing="ij")
+        pts = torch.stack([uu.reshape(-1), vv.reshape(-1)], -1)
+        for b0 in range(0, half, pair_chunk):
+            b1 = min(half, b0 + pair_chunk); n = b1 - b0
+            f2 = gaussian_blur_nchw(randn(n, C, h, w), 2.0)
+            f2 = (f2 / f2.flatten(2).std(dim=2).clamp_min(1e-6).view(n, C, 1, 1)).permute(0, 2, 3, 1).contiguous()
+            feat[half + b0:half + b1] = f2                                              # frame 2 of pair b = image b + half
+            fx, fy, ox, oy = [li[b0:b1, i:i + 1] for i in range(4)]
+            px_, py_ = pts[:, 0].unsqueeze(0).expand(n, -1), pts[:, 1].unsqueeze(0).expand(n, -1)
+            ray = torch.stack([(px_ - ox) / fx, (py_ - oy) / fy, torch.ones_like(px_)], 1)
+            p = ray / ray.norm(dim=1, keepdim=True)
+            xs, ys = px_ * (s_ / 2.0), py_ * (s_ / 2.0)                                 # level pixel -> half-resolution map coordinates
+            Dl = bilinear_zero_pad(depth[b0:b1].contiguous(), xs, ys)
+            Bl = bilinear_zero_pad(basis[b0:b1].contiguous(), xs, ys)
+            Dt = Dl + Bl @ W_true[b0:b1]
+            X = (R_true[b0:b1] @ p) * Dt.transpose(1, 2) + T_true[b0:b1]
+            u = fx * (X[:, 0] / X[:, 2]) + ox; v = fy * (X[:, 1] / X[:, 2]) + oy
+            feat[b0:b1] = bilinear_zero_pad(f2, u, v).reshape(n, h, w, C)               # frame 1 of pair b = image b
+        layers.append(feat)
+    R0 = torch.eye(3, device=dev, dtype=dtype).repeat(nimg, 1, 1)
+    T0 = torch.cat([T_true + randn(half, 3, 1) * start_trans_noise_m, -T_true + randn(half, 3, 1) * start_trans_noise_m], 0)
+    W0 = torch.zeros(nimg, K, 1, device=dev, dtype=dtype)
+    return ResizeScene(layers, basis, depth, intr, scales, R0, T0, W0)

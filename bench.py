@@ -37,6 +37,11 @@ LEVEL_IDS = (0, 1, 2, 3)
 H_FULL, W_FULL = 480, 640
 
 
+DTYPE_NAME = {"auto": "tf32 level-wise (tcgen05 kind::tf32 x3 below 65536 points/pair, x1 above; f32 accumulate; everything else f32)",
+              "levelwise": "tf32 level-wise (tcgen05 kind::tf32 x3 below 65536 points/pair, x1 above; f32 accumulate; everything else f32)",
+              "fp32": "f32", "tf32x1": "tf32x1 (f32 accumulate)", "tf32x2": "tf32x2 split-A (f32 accumulate)", "tf32x3": "tf32x3 split-A/R (f32-grade)"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -54,10 +59,11 @@ def parse():
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
-    ap.add_argument("--e2e-boundary", default="features", choices=["features", "concat"],
-                    help="host buffers of the e2e leg: 'features' = the layer boundary of the reference's BundleResize (bundlenet.py:376-399): "
-                         "feature maps in, [F2|gx|gy] derived on the device each step (banet_grad_fixed_concat); 'concat' = the 3C tensor itself")
-    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x1", "tf32x2", "tf32x3"],
+    ap.add_argument("--e2e-boundary", default="resize", choices=["resize", "features", "concat"],
+                    help="host buffers of the e2e leg: 'resize' = the reference's BundleResize boundary (bundlenet.py:332-399): the image batch's feature "
+                         "pyramid, half-resolution basis / depth and intrinsics in; conv1, conv2, p, D, B derived on the device (ResizeHostSolver); "
+                         "'features' = per-level tensors with F2 only ([F2|gx|gy] derived on the device); 'concat' = per-level tensors incl. the 3C tensor")
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "tf32x1", "tf32x2", "tf32x3", "levelwise"],
                     help="contraction path of the build kernel: auto = tensor cores (tcgen05 tf32 split-A) when K=128, else fp32 SIMT")
     return ap.parse_args()
 
@@ -122,22 +128,60 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_sample(C, K, reps, seed=1234):
-    """Times the oracle's materialised BundleIteration (reference-faithful: J,G,d tensors, matmul chain, LU) on ONE
-    pair at the 160x120 level (N = 19 200) in fp32 with all host threads; returns seconds per pair-iteration there."""
+def usable_cores():
+    """Threads this process may actually run on (cgroup / affinity aware; os.cpu_count() counts the whole host)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:                                           # cgroup v2 CPU quota, if any
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def cpu_reference_iteration(O, lv, mlp, R, T, W, chunk):
+    """One reference-faithful BundleIteration of ONE pair on the CPU, in point chunks so that a full 640x480 level fits in memory:
+    per chunk the reference's materialised tensors J [1,n,2,P], G [1,n,C,2], d [1,n,C,1] and the native op's product chain
+    (oracle.equation_construction == utils.cu:331-414), summed over chunks; then damping, LU solve and update (bundlenet.py:264-276)."""
+    fx, fy, ox, oy = lv.intr_tiled()
+    N = lv.N
+    AtA = Atb = None
+    rsum = 0
+    for a in range(0, N, chunk):
+        b = min(N, a + chunk)
+        _, _, _, aux = O.bundle_iteration(lv.conv1[:, a:b], lv.conv2, fx[:, a:b], fy[:, a:b], ox[:, a:b], oy[:, a:b], lv.p[:, :, a:b],
+                                          lv.D[:, a:b], lv.B[:, a:b], R, T, W, mlp, O.IterOptions(lambda_override=torch.ones(1)), return_aux=True)
+        AtA = aux["AtA"] if AtA is None else AtA + aux["AtA"]
+        Atb = aux["Atb"] if Atb is None else Atb + aux["Atb"]
+        rsum = rsum + aux["rbar"] * float(b - a)
+    avg = rsum / float(N)
+    lam = 1000.0 * torch.pow(torch.linalg.norm(avg, dim=-1, keepdim=True), 2.0 + O.lambda_mlp(avg, mlp))
+    diag = torch.diagonal(AtA, dim1=-2, dim2=-1)
+    dvec = torch.cat([diag[:, :-1] + 1e-5, torch.zeros(1, 1)], dim=-1)
+    sol = torch.linalg.solve(AtA + torch.diag_embed(dvec * lam.squeeze(-1)), Atb)
+    return O._update(sol[:, :6, :], R, T, O.IterOptions())
+
+
+def cpu_reference_sample(C, K, reps, seed=1234, level_id=3, chunk=38400):
+    """Times the oracle's reference-faithful BundleIteration (J, G, d tensors + the op's product chain + LU, torch-CPU fp32, all usable
+    host threads) on ONE WHOLE pair at the finest level (640x480, N = 307 200; chunked over points, nothing extrapolated within the
+    level).  Returns (seconds per pair-iteration per rep, N, threads)."""
     from oracle import ba_oracle as O
     from banet_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
-    sc = synth.make_scene(nb=1, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=(1,), seed=seed, dtype=torch.float32, device="cpu")
+    sc = synth.make_scene(nb=1, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=(level_id,), seed=seed, dtype=torch.float32, device="cpu")
     lv = sc.levels[0]
-    fx, fy, ox, oy = lv.intr_tiled()
     mlp = O.init_lambda_mlp(C, dtype=torch.float32)
     times = []
     with torch.no_grad():
         for i in range(reps + 1):
             t0 = time.perf_counter()
-            O.bundle_iteration(lv.conv1, lv.conv2, fx, fy, ox, oy, lv.p, lv.D, lv.B, sc.R0, sc.T0, sc.W0, mlp)
+            cpu_reference_iteration(O, lv, mlp, sc.R0, sc.T0, sc.W0, chunk)
             times.append(time.perf_counter() - t0)
     return times[1:], lv.N, cores        # first call is a warm-up
 
@@ -148,23 +192,31 @@ def pixels_per_pair_iter():
     return tot / len(LEVEL_IDS)
 
 
+def cpu_stats(times, n_sample, cores):
+    ts = sorted(times)
+    med = ts[len(ts) // 2]
+    scale = n_sample / pixels_per_pair_iter()          # a mean pair-iteration of the 4-level workload touches ΣN/4 points (per-point cost is level independent)
+    return {"value": scale / med, "unit": UNIT, "cores": cores, "kind": "port",
+            "min_med_max_s": [ts[0], med, ts[-1]], "reps": len(ts),
+            "sample": (f"oracle's reference-faithful BundleIteration (materialised J/G/d per point chunk + the op's product chain + LU), ONE whole pair "
+                       f"at 640x480 (N={n_sample}), fp32, {cores} threads (affinity/cgroup aware), {len(ts)} timed reps after 1 warm-up; value = "
+                       f"N/(ΣN/4) / median: a pair-iteration of the 4-level workload touches ΣN/4 points on average")}, med
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, args.steps)
+    reps = max(5, min(args.steps, 12))                 # bounded: a rep is one whole 640x480 pair-iteration (seconds)
     times, n_sample, cores = cpu_reference_sample(args.channels, args.bases, reps)
-    t = sorted(times)[len(times) // 2]
-    # pair-iterations/s at the workload's mean level size, extrapolated linearly in points (stated)
-    value = (n_sample / pixels_per_pair_iter()) / t
-    sample = (f"1 pair x 1 BundleIteration at 160x120 (N={n_sample}), C={args.channels}, K={args.bases}, fp32, "
-              f"median of {len(times)} runs, extrapolated linearly in points to the mean level size")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
-            "warmup": 1, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    cb, med = cpu_stats(times, n_sample, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+            "warmup": 1, "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args), "reference_arm": "oracle port (TF-1.x reference cannot execute here)"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "config": {"workload": workload_name(args), "reference_arm": "oracle port (the TF-1.x reference cannot execute here; its code is pinned to the "
+                                                                         "oracle through tests/test_oracle_pinned.py)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
@@ -201,7 +253,7 @@ def main():
             l.conv2 = l.conv2[..., :C].contiguous()
     levels = [ops.Level(l.conv1, l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid) for l in sc.levels]
     PREC = {"auto": _lib.PREC_AUTO, "fp32": _lib.PREC_FP32_SIMT, "tf32x1": _lib.PREC_TF32X1, "tf32x2": _lib.PREC_TF32X2,
-            "tf32x3": _lib.PREC_TF32X3}[args.precision]
+            "tf32x3": _lib.PREC_TF32X3, "levelwise": _lib.PREC_TF32_LEVELWISE}[args.precision]
     g = torch.Generator().manual_seed(7)
     dims = [C, 2 * C, 4 * C, 2 * C, C, 1]
     packed = []
@@ -228,21 +280,25 @@ def main():
     barrier()
     assert int(status.abs().max()) == 0, "solver reported a non-SPD / non-finite system"
 
-    # ---- accuracy of the timed precision mode on THIS workload: outputs against the FP32 SIMT path (pinned to the oracle by tests/) ----
+    # ---- accuracy of the timed precision mode on THIS workload: outputs against the FP32 SIMT path (which tests/test_gpu_default_precision.py
+    #      and tests/test_gpu_parity.py hold to the float64 oracle; the oracle itself does not fit a 32-pair 640x480 batch) -----------------
     precision_check = None
-    if rank == 0 and not args.no_precision_check and PREC != _lib.PREC_FP32_SIMT:
+    nvalid_frac = None
+    if rank == 0 and not args.no_precision_check:
         rf = lambda a, b: float(((a - b).norm() / b.norm()).item())
-        R1, T1, W1, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, precision=PREC)
-        R0_, T0_, W0_, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0,
-                                     precision=_lib.PREC_FP32_SIMT)
-        fin = sc.levels[-1]                      # the layer's depth output D + B.W (reference bundlenet.py:397) at the finest level
-        d1 = ops.depth_compose(fin.D.reshape(nb, -1), fin.B, W1); d0 = ops.depth_compose(fin.D.reshape(nb, -1), fin.B, W0_)
-        errs = {"R": rf(R1, R0_), "T": rf(T1, T0_), "depth": rf(d1, d0), "W": rf(W1, W0_)}
-        precision_check = {"vs": "fp32_simt path, same inputs, all levels x iterations", "rel_fro": errs, "tolerance": 1e-4,
-                           "ok": max(errs["R"], errs["T"], errs["depth"]) < 1e-4,
-                           "note": "north-star tolerance is on the pose / depth outputs; W (depth-basis coefficients) is reported as well"}
-        del d1, d0
-        del R1, T1, W1, R0_, T0_, W0_
+        fin = sc.levels[-1]
+        _, _, _, nv = ops.lm_build(levels[-1], sc.R0, sc.T0, sc.W0, precision=PREC)
+        nvalid_frac = float(nv.mean().item()) / fin.N
+        if PREC != _lib.PREC_FP32_SIMT:
+            R1, T1, W1, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, precision=PREC)
+            R0_, T0_, W0_, _ = ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0,
+                                         precision=_lib.PREC_FP32_SIMT)
+            d1 = ops.depth_compose(fin.D.reshape(nb, -1), fin.B, W1); d0 = ops.depth_compose(fin.D.reshape(nb, -1), fin.B, W0_)
+            errs = {"R": rf(R1, R0_), "T": rf(T1, T0_), "depth": rf(d1, d0), "W": rf(W1, W0_)}
+            precision_check = {"vs": "fp32_simt path (oracle-asserted in tests/), same inputs, all levels x iterations", "rel_fro": errs, "tolerance": 1e-4,
+                               "ok": max(errs.values()) < 1e-4,
+                               "note": "north-star tolerance 1e-4 on the pose / depth outputs; W (depth-basis coefficients) is held to it as well"}
+            del d1, d0, R1, T1, W1, R0_, T0_, W0_
     barrier()
 
     sampler = ClockSampler(local); sampler.start()
@@ -279,17 +335,22 @@ def main():
         by3c = by + nb * 4 * sl.N * 2 * C          # conv2 read as the reference lays it out: [F2|gx|gy] = 3C channels per texel
         per_level.append({"level": f"{sl.w}x{sl.h}", "ms": t * 1e3, "alg_bytes": by, "gbs": by / t / 1e9, "gbs_3c_layout": by3c / t / 1e9})
     top = per_level[-1]
-    traffic = None
+    # DRAM traffic of the dominant kernel per launch: from the committed ncu capture of THIS kernel / layout (profiles/lm_build_traffic.json,
+    # stamped with the commit and configuration it was taken on); null when the capture is of another kernel or layout
+    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else ("lm_build_tc7_kernel" if args.layout == "f2" else "lm_build_tc6_kernel")
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "lm_build_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            if tj.get("kernel") == kname and tj.get("layout") == args.layout and tj.get("nb") == nb:
+                traffic = tj.get("dram_bytes_per_launch")
+                traffic_src = {k: tj.get(k) for k in ("commit", "source", "precision")}
         except Exception:
             traffic = None
-    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else "lm_build_tc6_kernel"
     roofline = {"bound": "hbm", "kernel": f"{kname} (+lm_reduce_kernel) @640x480", "achieved": top["gbs"], "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": top["gbs"] / peak, "frac_3c_layout": top["gbs_3c_layout"] / peak,
-                "traffic": traffic, "per_level": per_level,
+                "traffic": traffic, "traffic_source": traffic_src, "per_level": per_level,
                 "all_levels_gbs": sum(p["alg_bytes"] for p in per_level) / sum(p["ms"] * 1e-3 for p in per_level) / 1e9}
 
     # ---- e2e: host buffers -> device -> solve -> host, through the public API -------------------------------
@@ -302,18 +363,16 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, n_sample, cores = cpu_reference_sample(C, K, 4)
-        t = sorted(times)[len(times) // 2]
-        cpu_baseline = {"value": (n_sample / pixels_per_pair_iter()) / t, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"oracle materialised BundleIteration, 1 pair at 160x120 (N={n_sample}), fp32, median of {len(times)}, "
-                                  f"{t:.2f} s each, extrapolated linearly in points"}
+        times, n_sample, cores = cpu_reference_sample(C, K, 5)
+        cpu_baseline, _ = cpu_stats(times, n_sample, cores)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_NAME[args.precision],
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_pairs": world * nb, "lm_iterations_per_step": total_iters,
                            "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": args.precision,
+                           "nvalid_fraction_finest_level": nvalid_frac,
                            "conv2_layout": "[F2|gx|gy] (3C channels, the reference's BundleIteration boundary)" if args.layout == "concat"
                                            else "F2 only (C channels); the kernel recomputes gx, gy on the fly (reference grad_fixed, bundlenet.py:92-100)",
                            "l2": "inputs (~33 GB/GPU) far exceed the 126 MB L2; no flush needed",
@@ -326,32 +385,48 @@ def main():
 
 
 def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
-    """The call a user with host-resident inputs makes: banet_b200.host_pipeline.HostSolver (pair chunks, H2D of chunk k+1
-    overlapping the solve of chunk k); every step copies every level tensor host->device and the result device->host."""
-    from banet_b200 import dist as bdist
-    from banet_b200.host_pipeline import HostSolver
+    """The call a user with host-resident inputs makes.  Default: banet_b200.host_pipeline.ResizeHostSolver at the reference's BundleResize
+    boundary; every step copies every input host->device and the result device->host (copies of later pair chunks overlap the solve)."""
+    from banet_b200 import dist as bdist, synth
+    from banet_b200.host_pipeline import HostSolver, ResizeHostSolver
     C = args.channels
-    feat = args.e2e_boundary == "features" and args.layout == "concat"
-    host = []
-    for l in sc.levels:
-        tens = {"grid": l.grid}
-        for name in ("conv1", "conv2", "intr", "p", "D", "B"):
-            t = getattr(l, name)
-            if name == "conv2" and feat:
-                t = t[..., :C].contiguous()
-            ht = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
-            ht.copy_(t)
-            tens[name] = ht
-        host.append(tens)
-    solver = HostSolver(host, derive_gradients=feat, chunks=args.e2e_chunks, device=dev, precision=prec)
-    hR = sc.R0.cpu().pin_memory(); hT = sc.T0.cpu().pin_memory(); hW = sc.W0.cpu().pin_memory()
+    rank = int(os.environ.get("RANK", "0"))
+    pin = lambda t: torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True).copy_(t)
+    if args.e2e_boundary == "resize":
+        rs = synth.make_resize_scene(args.nb, H_FULL, W_FULL, C, args.bases, level_ids=LEVEL_IDS, seed=4321 + 1000 * rank, device=dev)
+        solver = ResizeHostSolver([pin(l) for l in rs.layers], pin(rs.basis), pin(rs.init_depth), pin(rs.intr), rs.scales, chunks=args.e2e_chunks,
+                                  device=dev, precision=prec)
+        hR, hT, hW = pin(rs.R0), pin(rs.T0), pin(rs.W0)
+        del rs
+        torch.cuda.empty_cache()
+        boundary = ("the reference's BundleResize boundary (bundlenet.py:332-399): feature pyramid of the image batch (pair b = images b, b+nb/2), half-resolution "
+                    "basis and depth, intrinsics in pinned host memory; conv1 (zero copy), conv2 (F2 only), p, D, B derived on the device every step")
+        api = f"banet_b200.host_pipeline.ResizeHostSolver(chunks={args.e2e_chunks}).solve"
+    else:
+        feat = args.e2e_boundary == "features" and args.layout == "concat"
+        host = []
+        for l in sc.levels:
+            tens = {"grid": l.grid}
+            for name in ("conv1", "conv2", "intr", "p", "D", "B"):
+                t = getattr(l, name)
+                if name == "conv2" and feat:
+                    t = t[..., :C].contiguous()
+                tens[name] = pin(t)
+            host.append(tens)
+        solver = HostSolver(host, derive_gradients=feat, chunks=args.e2e_chunks, device=dev, precision=prec)
+        hR, hT, hW = pin(sc.R0), pin(sc.T0), pin(sc.W0)
+        boundary = ("per-level tensors: feature maps (C channels) + conv1, p, D, B, intr in pinned host memory; [F2|gx|gy] derived on the device every step "
+                    "(banet_grad_fixed_concat)") if feat else "every level tensor, conv2 as the 3C [F2|gx|gy] tensor, in pinned host memory"
+        api = f"banet_b200.host_pipeline.HostSolver(chunks={args.e2e_chunks}).solve"
     h2d = solver.h2d_bytes + (hR.numel() + hT.numel() + hW.numel()) * 4
     oR = torch.empty_like(hR).pin_memory(); oT = torch.empty_like(hT).pin_memory(); oW = torch.empty_like(hW).pin_memory()
     d2h = (oR.numel() + oT.numel() + oW.numel()) * 4 * world
+    last = {}
 
     def e2e_step():
         R, T, W, status = solver.solve(hR, hT, hW, args.iters, mlp_packed=packed, l2_regularizer_base=1000.0,
                                        out=None if world > 1 else (oR, oT, oW))
+        last["status"] = status
         if world > 1:
             R, T, W = bdist.all_gather_solution(R, T, W)
             return R.cpu(), T.cpu(), W.cpu()
@@ -360,6 +435,7 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
 
     e2e_step()
     torch.cuda.synchronize()
+    bad_pairs = int((last["status"] != 0).sum())
     if world > 1:
         import torch.distributed as td
         td.barrier(device_ids=[local])
@@ -374,13 +450,10 @@ def run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, prec):
         td.all_reduce(tms, op=td.ReduceOp.MAX); ms = float(tms.item())
     per = ms / args.e2e_steps * 1e-3
     return {"value": world * args.nb * total_iters / per, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
-            "d2h_bytes_per_step": d2h, "ms_per_step": per * 1e3, "steps": args.e2e_steps,
-            "boundary": ("feature maps (C channels) + conv1, p, D, B, intr in pinned host memory; [F2|gx|gy] derived on the device every step "
-                         "(banet_grad_fixed_concat), as the reference's BundleResize does (bundlenet.py:386-389)") if feat else
-                        "every level tensor, conv2 as the 3C [F2|gx|gy] tensor, in pinned host memory",
-            "api": f"banet_b200.host_pipeline.HostSolver(chunks={args.e2e_chunks}).solve",
-            "note": "pinned host -> device copy of every level tensor + solve + device -> host of (R,T,W) per step; copies of pair-chunk k+1 "
-                    "overlap the solve of chunk k"}
+            "d2h_bytes_per_step": d2h, "ms_per_step": per * 1e3, "steps": args.e2e_steps, "boundary": boundary, "api": api,
+            "pairs_with_skipped_steps": bad_pairs,
+            "note": "pinned host -> device copy of every input + solve + device -> host of (R,T,W) per step; copies of later pair chunks overlap the "
+                    "solve of the current one"}
 
 
 if __name__ == "__main__":

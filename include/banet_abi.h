@@ -150,6 +150,14 @@ int    banet_lm_solve_update(const float* H, const float* g, const float* lambda
                              float* R_out, float* T_out, float* W_out, float* delta, int32_t* status,
                              void* ws, size_t ws_bytes, banet_stream_t stream);
 
+/* banet_lm_lambda + banet_lm_solve_update in ONE launch (blocked Cholesky with the right-hand side as an extra row): what banet_lm_run
+ * executes per iteration.  mlp_weights NULL: lambda_in [nb] is used instead of the MLP.  lambda_out [nb] always receives the damping used.
+ * R_out/T_out/W_out may alias R/T/W.  opts->vmatrix_batch_scramble must be 0 (that option needs every pair's solution first). */
+int    banet_lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K,
+                     const float* mlp_weights, float base, const float* lambda_in, const banet_solve_opts_t* opts,
+                     const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+                     float* delta, float* lambda_out, int32_t* status, banet_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3b) Backward of one LM iteration — the gradient signature of the reference's BA layer: TF autodiff of
  *      bundlenet.py:193-278 with the registered op gradient EquationConstructionGrad (bundlenet.py:79-82,

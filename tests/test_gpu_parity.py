@@ -298,3 +298,43 @@ def test_cfg1_reference_cpu_case():
     assert rel_fro(R, oR) < TOL_OUT and rel_fro(T, oT) < TOL_OUT and rel_fro(W, oW) < TOL_OUT
     depth = ops.depth_compose(to_cuda32(lv.D).reshape(1, -1), to_cuda32(lv.B), W)
     assert rel_fro(depth, (a["D"] + a["B"] @ oW).reshape(1, -1)) < TOL_OUT
+
+
+@pytest.mark.parametrize("K,C", [(0, 8), (4, 8), (128, 128), (250, 16), (37, 5)])
+def test_lm_step_fused_lambda_solve_update(K, C):
+    """banet_lm_step (lambda-MLP + damping + blocked Cholesky with the rhs as an extra row + update, one launch) against float64 LU and the
+    oracle's lambda MLP / SE(3) update, and against the separate banet_lm_lambda + banet_lm_solve_update kernels."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(100 + K)
+    nb, P, N = 3, 6 + K, 700
+    A = torch.randn(nb, P, 3 * P, generator=g, dtype=torch.float64)
+    H = ((A @ A.transpose(1, 2)) / (3 * P)).float(); gv = (torch.randn(nb, P, generator=g, dtype=torch.float64) * 1e-2).float()
+    rbar_sum = torch.rand(nb, C, generator=g) * N * 0.2
+    mlp = mlp_for(C, 2)
+    base = 1000.0 if K else 1.0
+    R = O.angle_axis_rotation(*[torch.randn(nb, 1, 1, generator=g, dtype=torch.float64) * 0.1 for _ in range(3)]).float()
+    T = torch.randn(nb, 3, 1, generator=g); W = torch.randn(nb, K, 1, generator=g) if K else None
+    Rn, Tn, Wn, delta, lam, status = ops.lm_step(H.cuda(), gv.cuda(), rbar_sum.cuda(), N, ops.pack_mlp(mlp).cuda(), base, R.cuda(), T.cuda(), to_cuda32(W))
+    assert status.abs().max().item() == 0
+    avg = (rbar_sum.double() / N).unsqueeze(1)
+    olam = base * torch.pow(torch.linalg.norm(avg, dim=-1, keepdim=True), 2.0 + O.lambda_mlp(avg, mlp)).reshape(nb)
+    assert rel_fro(lam, olam) < 1e-4
+    Hd = H.double(); diag = torch.diagonal(Hd, dim1=1, dim2=2)
+    dvec = (diag + 1e-5) * lam.cpu().double().unsqueeze(-1)
+    if K:
+        dvec[:, -1] = 0
+    sol = torch.linalg.solve(Hd + torch.diag_embed(dvec), gv.double().unsqueeze(-1))
+    assert rel_fro(delta, sol.squeeze(-1)) < 1e-5
+    oR, oT = O._update(sol[:, :6], R.double(), T.double(), O.IterOptions())
+    assert rel_fro(Rn, oR) < 1e-6 and rel_fro(Tn, oT) < 1e-6
+    if K:
+        assert rel_fro(Wn, W.double() + sol[:, 6:]) < 1e-6
+    lam2 = ops.lm_lambda(rbar_sum.cuda(), N, ops.pack_mlp(mlp).cuda(), base)
+    R2, T2, W2, d2, st2 = ops.lm_solve_update(H.cuda(), gv.cuda(), lam2, R.cuda(), T.cuda(), to_cuda32(W), undamped_last=K > 0)
+    assert rel_fro(lam, lam2) < 1e-5 and rel_fro(delta, d2) < 1e-5 and rel_fro(Rn, R2) < 1e-6 and rel_fro(Tn, T2) < 1e-6
+    # a given lambda instead of the MLP, and a non-SPD matrix (flagged, step skipped)
+    Rn3, Tn3, Wn3, d3, lam3, st3 = ops.lm_step(H.cuda(), gv.cuda(), None, N, None, 1.0, R.cuda(), T.cuda(), to_cuda32(W), lam=lam2)
+    assert rel_fro(d3, d2) < 1e-5 and torch.equal(lam3, lam2)
+    Hbad = H.clone(); Hbad[1] = -Hbad[1]
+    Rb, Tb, Wb, db, lb, stb = ops.lm_step(Hbad.cuda(), gv.cuda(), None, N, None, 1.0, R.cuda(), T.cuda(), to_cuda32(W), lam=lam2)
+    assert stb.tolist()[1] == 1 and stb.tolist()[0] == 0 and float(db[1].abs().max()) == 0.0 and rel_fro(Tb[1], T[1]) < 1e-7

@@ -46,3 +46,33 @@ def test_host_solver_matches_device_solve(chunks, derive):
     # a different batch size moves the CTA / partial-slot boundaries: same maths, different fp32 summation order
     assert rel_fro(R, R1) < 1e-6 and rel_fro(T, T1) < 1e-5 and rel_fro(W, W1) < 1e-4
     assert torch.equal(oR, R.cpu()) and torch.equal(oT, T.cpu()) and torch.equal(oW, W.cpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunks", [2, 4])
+def test_resize_host_solver_matches_explicit_derivation(chunks):
+    """The BundleResize-boundary host pipeline (zero-copy conv1, other-half conv2, D/B/p derived on the device, chunked + overlapped copies)
+    against the same solve with every level tensor derived explicitly through the tested ops, and against the planted solution."""
+    from banet_b200 import ops, synth
+    from banet_b200.host_pipeline import ResizeHostSolver
+    from helpers import rel_fro
+    nimg, C, K = 8, 64, 128
+    sc = synth.make_resize_scene(nimg, 96, 128, C, K, level_ids=(2, 3), seed=41, device="cuda")
+    pin = lambda t: t.cpu().pin_memory()
+    hs = ResizeHostSolver([pin(l) for l in sc.layers], pin(sc.basis), pin(sc.init_depth), pin(sc.intr), sc.scales, chunks=chunks, precision=0)
+    R, T, W, st = hs.solve(pin(sc.R0), pin(sc.T0), pin(sc.W0), 4, lambda_fixed=0.05)
+    torch.cuda.synchronize()
+    assert int(st.abs().max()) == 0
+    half = nimg // 2
+    levels = []
+    for lay, s in zip(sc.layers, sc.scales):
+        h, w = lay.shape[1], lay.shape[2]
+        vv, uu = torch.meshgrid(torch.arange(h, device="cuda", dtype=torch.float32), torch.arange(w, device="cuda", dtype=torch.float32), indexing="ij")
+        pts = torch.stack([uu.reshape(-1), vv.reshape(-1)], -1).unsqueeze(0).repeat(nimg, 1, 1).contiguous()
+        conv1 = ops.resample(lay, pts, 1.0)                                   # reference: layer1 = resampler(layers[level], points / scale)
+        conv2 = torch.cat([lay[half:], lay[:half]], 0).contiguous()           # reference: the half swap
+        intr_l = sc.intr / s
+        levels.append(ops.Level(conv1, conv2, intr_l, ops.compute_coordinates(pts, intr_l, True), ops.resample(sc.init_depth, pts, s / 2.0),
+                                ops.resample(sc.basis, pts, s / 2.0), grid=(w, h)))
+    R1, T1, W1, st1 = ops.lm_run(levels, 4, sc.R0, sc.T0, sc.W0, lambda_fixed=0.05, precision=0)
+    assert rel_fro(R, R1) < 1e-6 and rel_fro(T, T1) < 1e-5 and rel_fro(W, W1) < 1e-4
