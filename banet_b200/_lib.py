@@ -37,6 +37,11 @@ class BanetTuning(C.Structure):
     _fields_ = [("tc_generation", C.c_int), ("tc7_force_direct", C.c_int), ("tc7_band_rows", C.c_int)]
 
 
+class BanetLegacyOpts(C.Structure):
+    """struct banet_legacy_opts (include/banet_abi.h): the module-level knobs of legacy/ba.py:5-8."""
+    _fields_ = [("early_termination", C.c_int), ("angle_change", C.c_float), ("translation_change", C.c_float), ("residual_ratio", C.c_float)]
+
+
 class BanetError(RuntimeError):
     pass
 
@@ -70,6 +75,9 @@ SIGNATURES = {
     "banet_depth_compose": (C.c_int, [c_float_p] * 3 + [C.c_int] * 3 + [c_float_p, c_stream]),
     "banet_lm_step": (C.c_int, [c_float_p] * 3 + [C.c_int] * 4 + [c_float_p, C.c_float, c_float_p, C.POINTER(BanetSolveOpts)] + [c_float_p] * 3
                       + [c_float_p] * 3 + [c_float_p, c_float_p, C.c_void_p, c_stream]),
+    "banet_lm_track_legacy_workspace_bytes": (C.c_size_t, [C.POINTER(BanetLevel), C.c_int]),
+    "banet_lm_track_legacy": (C.c_int, [C.POINTER(BanetLevel), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(BanetLegacyOpts)]
+                              + [c_float_p] * 2 + [C.c_void_p, c_float_p, C.c_void_p] + [C.c_void_p, C.c_size_t, c_stream]),
     "banet_lm_build_bwd": (C.c_int, [C.POINTER(BanetLevel)] + [c_float_p] * 6 + [C.c_int] + [c_float_p] * 7 + [c_stream]),
     "banet_lm_solve_update_bwd": (C.c_int, [c_float_p] * 4 + [C.c_int, C.c_int, C.POINTER(BanetSolveOpts)] + [c_float_p] * 5 + [c_float_p] * 6 + [c_stream]),
     "banet_grad_fixed_concat_bwd": (C.c_int, [c_float_p] + [C.c_int] * 5 + [c_float_p, c_stream]),

@@ -178,8 +178,8 @@ extern "C" int banet_lm_step(const float* H, const float* g, const float* rbar_s
     BANET_REQUIRE((mlp_weights && rbar_sum && N > 0 && C > 0) || lambda_in, BANET_ERR_BAD_ARG, "lm_step: needs lambda-MLP weights + rbar_sum, or lambda_in");
     BANET_REQUIRE(K == 0 || (W && W_out), BANET_ERR_BAD_ARG, "lm_step: K=%d but W is null", K);
     BANET_REQUIRE(!opts->vmatrix_batch_scramble, BANET_ERR_UNSUPPORTED, "lm_step: vmatrix_batch_scramble needs the separate banet_lm_solve_update");
-    return lm_step(H, g, rbar_sum, nb, N, C > 0 ? C : 1, K, mlp_weights, base, lambda_in, *opts, R, T, W, R_out, T_out, W_out, delta, lambda_out, status, 0,
-                   (cudaStream_t)stream);
+    return lm_step(H, g, rbar_sum, nb, N, C > 0 ? C : 1, K, mlp_weights, base, mlp_weights ? nullptr : lambda_in, kStepBundleNet, nullptr, *opts, R, T, W,
+                   R_out, T_out, W_out, delta, lambda_out, status, 0, (cudaStream_t)stream);
 }
 
 extern "C" int banet_lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W,
@@ -284,8 +284,8 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
             if (rc) return rc;
             const int P = 6 + K;
             if (!opts->vmatrix_batch_scramble && lm_step_supported(P, lv->C)) {      // one launch: lambda-MLP + damping + Cholesky + update
-                rc = lm_step(H, g, rbar, nb, lv->N, lv->C, K, use_mlp ? mlp_weights[l] : nullptr, l2_regularizer_base, lam, *opts,
-                             R, T, W, R, T, W, delta, lam, status, 1, st);
+                rc = lm_step(H, g, rbar, nb, lv->N, lv->C, K, use_mlp ? mlp_weights[l] : nullptr, l2_regularizer_base, use_mlp ? nullptr : lam,
+                             kStepBundleNet, nullptr, *opts, R, T, W, R, T, W, delta, lam, status, 1, st);
                 if (rc) return rc;
                 continue;
             }
@@ -299,4 +299,25 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
     }
     BANET_CUDA_LAUNCH_CHECK("lm_run");
     return BANET_OK;
+}
+
+extern "C" size_t banet_lm_track_legacy_workspace_bytes(const banet_level_t* levels, int nlevels)
+{
+    if (!levels || nlevels <= 0) return 0;
+    for (int l = 0; l < nlevels; ++l) if (check_level(&levels[l], "lm_track_legacy") || levels[l].K != 0) return 0;
+    return lm_track_legacy_workspace_bytes(levels, nlevels);
+}
+
+extern "C" int banet_lm_track_legacy(const banet_level_t* levels, int nlevels, const int* level_iters, const float* const* mlp_weights,
+                                     const banet_legacy_opts_t* opts, float* R, float* T, int32_t* iters_done, float* valid_ratio, int32_t* status,
+                                     void* ws, size_t ws_bytes, banet_stream_t stream)
+{
+    BANET_REQUIRE(levels && nlevels > 0 && level_iters && opts && R && T && valid_ratio && status, BANET_ERR_BAD_ARG, "lm_track_legacy: bad argument");
+    for (int l = 0; l < nlevels; ++l) {
+        int rc = check_level(&levels[l], "lm_track_legacy");
+        if (rc) return rc;
+        BANET_REQUIRE(levels[l].K == 0 && levels[l].nb == levels[0].nb && levels[l].conv2_channels == 3 * levels[l].C && level_iters[l] >= 0, BANET_ERR_BAD_ARG,
+                      "lm_track_legacy: level %d must be pose-only (K=0) with the [F2|gx|gy] layout and the same batch size", l);
+    }
+    return lm_track_legacy(levels, nlevels, level_iters, mlp_weights, *opts, R, T, iters_done, valid_ratio, status, ws, ws_bytes, (cudaStream_t)stream);
 }

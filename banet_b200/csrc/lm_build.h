@@ -54,10 +54,17 @@ int lm_solve_update(const float* H, const float* g, const float* lambda, int nb,
                     float* delta, int32_t* status, int status_accumulate, cudaStream_t st);
 
 // fused lambda-MLP + damping + blocked Cholesky + update, one launch (lm_step.cu); mlp == nullptr: lambda_in is used as is
+struct StepMode { float lambda_exp0; int rbar_per_valid, use_vmatrix, clamp_theta; };
+constexpr StepMode kStepBundleNet = {2.0f, 0, 1, 1};          // bundlenet.py:241-276
 bool lm_step_supported(int P, int C);
 int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K, const float* mlp, float base, const float* lambda_in,
-            const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+            const StepMode& mode, const float* nvalid, const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
             float* delta, float* lambda_out, int32_t* status, int status_accumulate, cudaStream_t st);
+
+// legacy pose-only tracker loop with device-side accept / reject and early termination (lm_legacy.cu)
+size_t lm_track_legacy_workspace_bytes(const banet_level_t* levels, int nlevels);
+int lm_track_legacy(const banet_level_t* levels, int nlevels, const int* level_iters, const float* const* mlp_weights, const banet_legacy_opts_t& o,
+                    float* R, float* T, int32_t* iters_done, float* valid_ratio, int32_t* status, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // backward of one iteration (lm_bwd.cu)
 int lm_build_bwd(const banet_level_t* lv, const float* R, const float* T, const float* W, const float* dH, const float* dg, const float* drbar,

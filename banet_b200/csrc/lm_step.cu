@@ -68,7 +68,8 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ in, const 
 template <typename S>
 __global__ void __launch_bounds__(STEP_THREADS)
 lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const float* __restrict__ rbar_sum, int N, int C,
-               const float* __restrict__ mlp, float base, const float* __restrict__ lambda_in, int P, float eps, int ndamped,
+               const float* __restrict__ mlp, float base, const float* __restrict__ lambda_in, const StepMode mode, const float* __restrict__ nvalid,
+               int P, float eps, int ndamped,
                const float* __restrict__ R, const float* __restrict__ T, const float* __restrict__ W,
                float* __restrict__ R_out, float* __restrict__ T_out, float* __restrict__ W_out,
                float* __restrict__ delta, float* __restrict__ lambda_out, int32_t* __restrict__ status, int status_accumulate)
@@ -87,9 +88,10 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
 
     // ---- 1. lambda -------------------------------------------------------------------------------------------------------------------
     float lam;
-    if (mlp) {
+    if (!lambda_in) {
         float* bufA = mbuf; float* bufB = mbuf + 4 * C; float* acc = mbuf + 8 * C;
-        const float invN = 1.0f / (float)N;
+        // bundlenet.py:243 divides by N; the legacy tracker rescales by N / valid, i.e. divides by the in-bounds count (legacy/ba.py:256,274)
+        const float invN = 1.0f / (mode.rbar_per_valid ? nvalid[b] : (float)N);
         float part = 0.f;
         for (int c = tid; c < C; c += STEP_THREADS) { const float r = rbar_sum[(size_t)b * C + c] * invN; bufA[c] = r; part += r * r; }
         for (int c = tid; c < 4 * C; c += STEP_THREADS) acc[c] = 0.f;
@@ -99,7 +101,7 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         const int dims[6] = {C, 2 * C, 4 * C, 2 * C, C, 1};
         const float* wp = mlp;
         float* in = bufA; float* out = bufB;
-        for (int l = 0; l < 5; ++l) {
+        for (int l = 0; l < (mlp ? 5 : 0); ++l) {
             const int cin = dims[l], cout = dims[l + 1];
             dense_layer(in, wp, wp + (size_t)cin * cout, cin, cout, l == 4, acc, out, tid);
             for (int c = tid; c < cout; c += STEP_THREADS) acc[c] = 0.f;       // ready for the next layer (visible after its first barrier)
@@ -107,7 +109,8 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
             float* tmp = in; in = out; out = tmp;
             __syncthreads();
         }
-        if (tid == 0) { s_lam = base * powf(sqrtf(s_norm2), 2.0f + in[0]); lambda_out[b] = s_lam; }   // bundlenet.py:249,253
+        // bundlenet.py:249,253: base * ||rbar||^(2 + h); legacy/ba.py:280: ||rbar||^(1 + h); no MLP (legacy/ba.py:190): h = 0
+        if (tid == 0) { s_lam = base * powf(sqrtf(s_norm2), mode.lambda_exp0 + (mlp ? in[0] : 0.f)); lambda_out[b] = s_lam; }
         __syncthreads();
         lam = s_lam;
     } else {
@@ -221,7 +224,7 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         for (int i = 0; i < 6; ++i) { float dv = flag ? 0.f : (float)xs[i]; if (!isfinite(dv)) dv = 0.f; dl[i] = (double)dv; }
         const double wx = dl[0], wy = dl[1], wz = dl[2], tx = dl[3], ty = dl[4], tz = dl[5];
         const double th_raw = sqrt(wx * wx + wy * wy + wz * wz);
-        const double th = fmax(th_raw, 1e-6);                        // AngleaAxisRotation (bundlenet.py:17-37)
+        const double th = mode.clamp_theta ? fmax(th_raw, 1e-6) : fmax(th_raw, 1e-300);      // AngleaAxisRotation (bundlenet.py:17-37; legacy/ba.py:60-80 has no clamp)
         const double kx = wx / th, ky = wy / th, kz = wz / th, c = cos(th), s = sin(th), oc = 1.0 - c;
         const double dr[9] = {c + kx * kx * oc,      kx * ky * oc - kz * s, ky * s + kx * kz * oc,
                               kz * s + kx * ky * oc, c + ky * ky * oc,      -kx * s + ky * kz * oc,
@@ -241,8 +244,8 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         for (int i = 0; i < 3; ++i) {
             for (int j = 0; j < 3; ++j)
                 R_out[(size_t)b * 9 + i * 3 + j] = (float)(dr[i * 3] * Rin[j] + dr[i * 3 + 1] * Rin[3 + j] + dr[i * 3 + 2] * Rin[6 + j]);
-            T_out[(size_t)b * 3 + i] = (float)(V[i * 3] * tx + V[i * 3 + 1] * ty + V[i * 3 + 2] * tz
-                                               + dr[i * 3] * Tin[0] + dr[i * 3 + 1] * Tin[1] + dr[i * 3 + 2] * Tin[2]);
+            const double vt = mode.use_vmatrix ? (V[i * 3] * tx + V[i * 3 + 1] * ty + V[i * 3 + 2] * tz) : dl[3 + i];     // legacy/ba.py:213: T' = t + dr T
+            T_out[(size_t)b * 3 + i] = (float)(vt + dr[i * 3] * Tin[0] + dr[i * 3 + 1] * Tin[1] + dr[i * 3 + 2] * Tin[2]);
         }
     }
 }
@@ -255,9 +258,10 @@ size_t lm_step_smem(int P, int C, bool use_double)
 
 bool lm_step_supported(int P, int C) { return lm_step_smem(P, C, false) <= 220 * 1024; }
 
-// mlp == nullptr: lambda_in [nb] is used as is.  In-place R/T/W (R_out == R ...) is fine: a pair's CTA reads before it writes.
+// lambda_in != nullptr: used as is; else lambda = base * ||rbar||^(exp0 + MLP(rbar)) (MLP term 0 when mlp == nullptr).
+// In-place R/T/W (R_out == R ...) is fine: a pair's CTA reads before it writes.
 int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N, int C, int K, const float* mlp, float base, const float* lambda_in,
-            const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
+            const StepMode& mode, const float* nvalid, const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
             float* delta, float* lambda_out, int32_t* status, int status_accumulate, cudaStream_t st)
 {
     const int P = 6 + K;
@@ -269,12 +273,12 @@ int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N
     if (use_double) {
         e = cudaFuncSetAttribute(lm_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-        lm_step_kernel<double><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, P, opts.damping_eps, ndamped, R, T, W,
+        lm_step_kernel<double><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, mode, nvalid, P, opts.damping_eps, ndamped, R, T, W,
                                                                R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
     } else {
         e = cudaFuncSetAttribute(lm_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-        lm_step_kernel<float><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, P, opts.damping_eps, ndamped, R, T, W,
+        lm_step_kernel<float><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, mode, nvalid, P, opts.damping_eps, ndamped, R, T, W,
                                                               R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
     }
     BANET_CUDA_LAUNCH_CHECK("lm_step_kernel launch");

@@ -351,3 +351,34 @@ def depth_compose_bwd(dout: Tensor, basis: Tensor, W: Tensor):
     dbasis = torch.empty_like(bs); dW = torch.empty(nb, K, 1, device=bs.device)
     check(lib.banet_depth_compose_bwd(g.data_ptr(), bs.data_ptr(), Wt.data_ptr(), nb, M, K, dbasis.data_ptr(), dW.data_ptr(), _stream()), "banet_depth_compose_bwd")
     return dbasis, dW
+
+
+# ------------------------------------------------------------------------------------------ legacy tracker loop
+def lm_track_legacy(levels: Sequence[Level], level_iters: Sequence[int], R: Tensor, T: Tensor, mlp_packed: Optional[Sequence[Optional[Tensor]]] = None,
+                    early_termination: bool = True, angle_change: float = 0.002 * (3.14 / 180.0), translation_change: float = 0.0002,
+                    residual_ratio: float = 1.0):
+    """banet_lm_track_legacy (legacy/ba.py:83-145 on the device) -> R, T, iters_done [nlevels,nb], valid_ratio [nb], status [nb]."""
+    lib = load()
+    structs, keep = [], []
+    for lv in levels:
+        s, k = lv.as_struct(); structs.append(s); keep.append(k)
+    arr = (BanetLevel * len(structs))(*structs)
+    nb = structs[0].nb
+    R = _chk(R, "R", (nb, 3, 3)).clone(); T = _chk(T, "T", (nb, 3, 1)).clone()
+    iters = (C.c_int * len(structs))(*[int(i) for i in level_iters])
+    mlp_ptrs = (C.c_void_p * len(structs))()
+    for i in range(len(structs)):
+        m = None if mlp_packed is None else mlp_packed[i]
+        if m is not None:
+            m = _chk(m, "mlp_packed"); keep.append(m)
+        mlp_ptrs[i] = None if m is None else m.data_ptr()
+    opts = _lib.BanetLegacyOpts(int(early_termination), float(angle_change), float(translation_change), float(residual_ratio))
+    nbytes = lib.banet_lm_track_legacy_workspace_bytes(arr, len(structs))
+    if nbytes == 0:
+        check(-1, "banet_lm_track_legacy_workspace_bytes")
+    ws = _ws(nbytes, R.device)
+    done = torch.zeros(len(structs), nb, device=R.device, dtype=torch.int32)
+    ratio = torch.zeros(nb, device=R.device); status = torch.empty(nb, device=R.device, dtype=torch.int32)
+    check(lib.banet_lm_track_legacy(arr, len(structs), iters, mlp_ptrs, C.byref(opts), R.data_ptr(), T.data_ptr(), done.data_ptr(), ratio.data_ptr(),
+                                    status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_track_legacy")
+    return R, T, done, ratio, status

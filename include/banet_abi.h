@@ -205,6 +205,25 @@ int    banet_lm_run(const banet_level_t* levels, int nlevels, int iters_per_leve
                     float* R, float* T, float* W, int32_t* status,
                     void* ws, size_t ws_bytes, banet_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (4) The legacy pose-only keyframe tracker loop: legacy/ba.py:83-145 (`Tracker.trackTF`) with CameraIteration (:147-214) or, with
+ *     early termination, CameraIteration2 (:226-345: lambda-MLP step, residual re-evaluated at the updated pose, step kept only if it
+ *     decreased) — accept / reject and the per-level termination test run on the device, per pair, without host synchronisation.
+ *     levels[l]: pose-only (K = 0, B NULL), conv2 = [F2|gx|gy]; level_iters[l] = maximum iterations at level l.
+ *     iters_done [nlevels,nb] (optional): CameraIteration2 calls each pair actually made per level.
+ *     valid_ratio [nb]: what the reference returns as `ratio` — N / valid of the last executed CameraIteration2, or valid / N (plain).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct banet_legacy_opts {
+    int   early_termination;     /* legacy/ba.py:5  (True)                  */
+    float angle_change;          /* legacy/ba.py:6  0.002 * (3.14 / 180)    */
+    float translation_change;    /* legacy/ba.py:7  0.0002                  */
+    float residual_ratio;        /* legacy/ba.py:8  1.0                     */
+} banet_legacy_opts_t;
+size_t banet_lm_track_legacy_workspace_bytes(const banet_level_t* levels, int nlevels);
+int    banet_lm_track_legacy(const banet_level_t* levels, int nlevels, const int* level_iters, const float* const* mlp_weights,
+                             const banet_legacy_opts_t* opts, float* R, float* T, int32_t* iters_done, float* valid_ratio,
+                             int32_t* status, void* ws, size_t ws_bytes, banet_stream_t stream);
+
 /* Final depth composition of BundleResize (bundlenet.py:397): out = init_depth + basis . W
  *   basis [nb,M,K] (M = h/2*w/2), W [nb,K,1], init_depth [nb,M] -> out [nb,M] */
 int banet_depth_compose(const float* init_depth, const float* basis, const float* W, int nb, int M, int K,
