@@ -9,7 +9,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbanet_sm100.so")
+LIB_PATH = os.environ.get("BANET_LIB_PATH") or os.path.join(_HERE, "libbanet_sm100.so")      # the override is for kernel-variant timing scripts only
 
 BANET_OK = 0
 PREC_AUTO, PREC_FP32_SIMT, PREC_TF32X1, PREC_TF32X2, PREC_TF32X3, PREC_TF32_LEVELWISE = -1, 0, 1, 2, 3, 4

@@ -45,8 +45,10 @@ static int levelwise_mode(const banet_level_t* lv) { return lv->N < 65536 ? BANE
 int resolve_precision(const banet_level_t* lv, int precision)
 {
     if (precision == BANET_PREC_AUTO) {
+        // AUTO = the level-wise policy: measured on the cfg2 bench workload (32 pairs, 20 iterations, against the FP32 path; profiles/r02_*):
+        // W 4.2e-6 / depth 5.8e-7 where TF32X2 everywhere gives 2.6e-4 / 3.5e-5 and TF32X1 3.6e-4 / 5.0e-5 -- and it is the fastest of the three.
         if (!tc_supported(lv)) return BANET_PREC_FP32_SIMT;
-        return BANET_PREC_TF32X2;
+        return lv->K == 128 ? levelwise_mode(lv) : BANET_PREC_TF32X2;       // K = 64 / 32: the single-pass mode is not instantiated
     }
     if (precision == BANET_PREC_TF32_LEVELWISE) {
         if (!tc_supported(lv)) return BANET_PREC_FP32_SIMT;

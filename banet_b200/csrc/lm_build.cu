@@ -87,11 +87,16 @@ lm_build_kernel(const BuildParams prm)
     const bool fly_grad = (c2 == C);
 
     // ---- accumulators (persist across the tiles of one pair) -----------------------------------
-    constexpr int T  = KP / 16;                 // per-thread H_dd tile edge
+    // K > 128 (KP = 256): one launch per 128 x 128 block (prm.kq_i, prm.kq_j) of H_dd's lower triangle; the staged tile, the depth update and
+    // the gather are those of the full basis, the register tile is that of K = 128 (a 16 x 16 tile would need 256 accumulators per thread)
+    constexpr int KB = (KP > 128) ? 128 : KP;   // contraction block edge
+    const int ki0 = (KP > 128) ? prm.kq_i * 128 : 0, kj0 = (KP > 128) ? prm.kq_j * 128 : 0;
+    const bool first_block = (KP <= 128) || (prm.kq_i == 0 && prm.kq_j == 0), diag_block = (KP <= 128) || (prm.kq_i == prm.kq_j);
+    constexpr int T  = KB / 16;                 // per-thread H_dd tile edge
     constexpr int G  = (T >= 4) ? 4 : (T > 0 ? T : 1);
     constexpr int NG = (T > 0) ? T / G : 0;
     constexpr int TT = (T > 0) ? T : 1;
-    constexpr int NPART = (KP > 0) ? BUILD_THREADS / KP : 1;
+    constexpr int NPART = (KP > 0) ? BUILD_THREADS / KB : 1;
     constexpr int EA = (KP > 0) ? (7 + NPART - 1) / NPART : 1;
     float acc[TT][TT];
     float accx[EA];
@@ -116,18 +121,20 @@ lm_build_kernel(const BuildParams prm)
         if constexpr (KP > 0) {
 #pragma unroll
             for (int e = 0; e < TT; ++e) {
-                const int row = (e / G) * (16 * G) + G * ti + (e % G);
+                const int row = ki0 + (e / G) * (16 * G) + G * ti + (e % G);
 #pragma unroll
                 for (int f = 0; f < TT; ++f) {
-                    const int col = (f / G) * (16 * G) + G * tj + (f % G);
+                    const int col = kj0 + (f / G) * (16 * G) + G * tj + (f % G);
                     if (row < K && col < K) slot[row * K + col] = acc[e][f];
                 }
             }
-            const int k = tid % KP, part = tid / KP;
+            const int k = kj0 + tid % KB, part = tid / KB;
+            if (diag_block) {
 #pragma unroll
-            for (int q = 0; q < EA; ++q) {
-                const int r = part * EA + q;
-                if (r < 7 && k < K) slot[L.off_ext() + r * K + k] = accx[q];
+                for (int q = 0; q < EA; ++q) {
+                    const int r = part * EA + q;
+                    if (r < 7 && k < K) slot[L.off_ext() + r * K + k] = accx[q];
+                }
             }
         }
         // cc: 28 values held by threads 0..63 -> warp reduce, combine the two warps through smem
@@ -137,12 +144,14 @@ lm_build_kernel(const BuildParams prm)
         }
         // rbar: sRb holds one row of per-channel |diff| sums per warp (accumulated in S2)
         __syncthreads();
-        if (tid < 28) slot[L.off_cc() + tid] = sCC[tid] + sCC[32 + tid];
-        for (int c = tid; c < C; c += BUILD_THREADS) {
-            float s = 0.f;
+        if (first_block) {
+            if (tid < 28) slot[L.off_cc() + tid] = sCC[tid] + sCC[32 + tid];
+            for (int c = tid; c < C; c += BUILD_THREADS) {
+                float s = 0.f;
 #pragma unroll
-            for (int wq = 0; wq < BUILD_WARPS; ++wq) s += sRb[wq * C + c];
-            slot[L.off_rbar() + c] = s;
+                for (int wq = 0; wq < BUILD_WARPS; ++wq) s += sRb[wq * C + c];
+                slot[L.off_rbar() + c] = s;
+            }
         }
         __syncthreads();
     };
@@ -340,7 +349,7 @@ lm_build_kernel(const BuildParams prm)
         // ---- S4: basis contraction  H_dd += s b b^T,  [H_cd; g_d] += [v; t] b^T  (fp32 FFMA) ------
         if constexpr (KP > 0) {
             __syncthreads();
-            const int k = tid % KP, part = tid / KP;
+            const int k = kj0 + tid % KB, part = tid / KB;
 #pragma unroll 2
             for (int n = 0; n < cnt; ++n) {
                 if (rec[R_MASK * TILE_PX + n] == 0.f) continue;
@@ -351,8 +360,8 @@ lm_build_kernel(const BuildParams prm)
                 float a[TT], cvals[TT];
 #pragma unroll
                 for (int gq = 0; gq < NG; ++gq) {
-                    lds_group<G>(Bs + n * LDB + gq * 16 * G + G * ti, a + gq * G);
-                    lds_group<G>(Bs + n * LDB + gq * 16 * G + G * tj, cvals + gq * G);
+                    lds_group<G>(Bs + n * LDB + ki0 + gq * 16 * G + G * ti, a + gq * G);
+                    lds_group<G>(Bs + n * LDB + kj0 + gq * 16 * G + G * tj, cvals + gq * G);
                 }
 #pragma unroll
                 for (int e = 0; e < TT; ++e) {
@@ -448,13 +457,14 @@ static int padded_K(int K) {
     if (K <= 32) return 32;
     if (K <= 64) return 64;
     if (K <= 128) return 128;
+    if (K <= 256) return 256;
     return -1;
 }
 
 int build_plan(const banet_level_t* lv, int num_sms, BuildPlan* plan)
 {
     const int KP = padded_K(lv->K);
-    BANET_REQUIRE(KP >= 0, BANET_ERR_UNSUPPORTED, "lm_build (fp32 SIMT): K=%d > 128 not supported on this path", lv->K);
+    BANET_REQUIRE(KP >= 0, BANET_ERR_UNSUPPORTED, "lm_build (fp32 SIMT): K=%d > 256 not supported", lv->K);
     BANET_REQUIRE(lv->C <= 2048, BANET_ERR_UNSUPPORTED, "lm_build: C=%d > 2048", lv->C);
     plan->KP = KP;
     plan->tiles_per_pair = (lv->N + TILE_PX - 1) / TILE_PX;
@@ -494,6 +504,7 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
     prm.partials = reinterpret_cast<float*>(ws);
     prm.slot_floats = plan.slot_floats; prm.max_span = plan.max_span;
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
+    prm.kq_i = 0; prm.kq_j = 0;
     prm.grid_w = 0; prm.grid_h = 0; prm.tiles_x = 0; prm.tiles_y = 0; prm.band_rows = 1; prm.hdd_transposed = 0; prm.force_direct = 0; prm.trace = nullptr;
     const bool vec4 = (lv->C % 4 == 0) && (lv->conv2_channels % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(lv->conv1) | reinterpret_cast<uintptr_t>(lv->conv2)) % 16 == 0);
@@ -506,6 +517,13 @@ int lm_build_simt(const banet_level_t* lv, const BuildPlan& plan, const float* R
         case 32:  BANET_DISPATCH(32); break;
         case 64:  BANET_DISPATCH(64); break;
         case 128: BANET_DISPATCH(128); break;
+        case 256:                    // lower-triangle 128-blocks (0,0), (1,0), (1,1); lm_reduce mirrors
+            rc = BANET_OK;
+            for (int blk = 0; blk < 3 && rc == BANET_OK; ++blk) {
+                prm.kq_i = blk == 0 ? 0 : 1; prm.kq_j = blk == 2 ? 1 : 0;
+                BANET_DISPATCH(256);
+            }
+            break;
         default: set_error("lm_build: bad KP %d", plan.KP); return BANET_ERR_UNSUPPORTED;
     }
 #undef BANET_DISPATCH

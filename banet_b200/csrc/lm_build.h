@@ -11,6 +11,7 @@ struct BuildParams {
     int slot_floats, max_span, tiles_per_pair;
     long long total_tiles;
     int grid_w, grid_h, tiles_x, tiles_y;   // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
+    int kq_i, kq_j;                   // fp32 SIMT path, K > 128: the 128 x 128 block of H_dd this launch computes
     int band_rows;                    // generation 7: tiles are walked in bands of this many tile rows, column by column inside a band
     int hdd_transposed;               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
     int force_direct;                 // generation 7, testing: take the global-tap fallback for every tile

@@ -47,6 +47,12 @@ constexpr int CHAIN = 8, TMEM_COLS = 512, ACCL = 320;
 constexpr int CHK = 32;                                         // channels per staged chunk: one texel chunk = 128 B = all 32 banks
 constexpr int WX = BANET_TC7_WX, WY = BANET_TC7_WY;             // staged window (texels); an 8x8 tile needs >= 11..12 at unit zoom
 constexpr int WIN_BYTES = WX * WY * CHK * 4;
+#ifdef BANET_TC7_DBG_BOXY            // timing experiment only: the TMA box has fewer rows than the window (results are garbage)
+constexpr int BOX_Y = BANET_TC7_DBG_BOXY;
+#else
+constexpr int BOX_Y = WY;
+#endif
+constexpr int WIN_TX_BYTES = WX * BOX_Y * CHK * 4;
 
 template <int MODE, int NCH> struct Smem {
     static_assert(MODE == 1 || MODE == 2, "generation 7 implements TF32X1 and TF32X2 (TF32X3 stays on generation 6: no room for the windows)");
@@ -343,9 +349,13 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             const int jt = q / NCHK, c = q - jt * NCHK, buf = q % NWB;
             mbar_wait_parked(&recs[jt % NREC], (jt / NREC) & 1);
             int wx0, wy0;
+#ifdef BANET_TC7_DBG_NOTMA          // timing experiment only: staged tiles complete without loading anything (results are garbage)
+            if (false) {
+#else
             if (decide(jt, wx0, wy0)) {
+#endif
                 const int b = sTile[(jt % NREC) * 4];
-                mbar_arrive_expect_tx(&winfull[buf], WIN_BYTES);
+                mbar_arrive_expect_tx(&winfull[buf], WIN_TX_BYTES);
                 tma_load_4d(base + SM::off_win + buf * WIN_BYTES, &tmapF, c * CHK, wx0, wy0, b, &winfull[buf]);
             } else {
                 mbar_arrive(&winfull[buf]);                   // direct-tap tile: nothing to stage, the phase completes at once
@@ -388,7 +398,11 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                 const int q = j * NCHK + c, buf = q % NWB;
                 mbar_wait_parked(&winfull[buf], (q / NWB) & 1);
                 float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef BANET_TC7_DBG_NOGATHER       // timing experiment only: no tap loads / arithmetic (results are garbage)
+                if (false) {
+#else
                 if (mask != 0.f) {
+#endif
                     // grad_fixed on the fly (bundlenet.py:92-100): gx, gy = 0.5 * central differences at the 4 bilinear taps.  Two phases so that
                     // at most 8 of the 12 taps are live at once (88-register budget): A = the two middle rows (f2, gx and the part of gy they
                     // carry), B = the rows above / below.  The empty asm ties phase B's first address to a phase-A result: ptxas may not hoist
@@ -709,7 +723,7 @@ static int launch7(const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildPa
 }  // namespace v7
 
 bool lm_build_tc7_supported(int mode, int nch, int kblk) { return (mode == 1 || mode == 2) && (nch == 1 || nch == 2) && kblk == 4; }
-void lm_build_tc7_window(int* wx, int* wy) { *wx = v7::WX; *wy = v7::WY; }
+void lm_build_tc7_window(int* wx, int* wy) { *wx = v7::WX; *wy = v7::BOX_Y; }
 
 int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildParams& prm, int grid, cudaStream_t st)
 {

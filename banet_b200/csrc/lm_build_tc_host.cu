@@ -95,7 +95,7 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
     prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h;
     prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0; prm.tiles_y = lv->grid_h > 0 ? (lv->grid_h + 7) / 8 : 0;
-    prm.band_rows = 1;
+    prm.band_rows = 1; prm.kq_i = 0; prm.kq_j = 0;
     prm.hdd_transposed = 1;
     prm.force_direct = g_tuning.tc7_force_direct;
     prm.trace = nullptr;

@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=["cfg2", "cfg4", "cfg5"],
+                    help="BASELINE.json configs: cfg2 (default; the metric's workload, also cfg3 under torchrun), cfg4 = 5-frame window as 4 pairs, dense + "
+                         "sparse 4096-point variants, 10 iterations per level; cfg5 = K sweep {32,64,128,256} at 640x480, nb=64, tensor cores vs fp32 SIMT")
     ap.add_argument("--nb", type=int, default=32, help="frame-pairs per GPU")
     ap.add_argument("--channels", type=int, default=128)
     ap.add_argument("--bases", type=int, default=128)
@@ -226,11 +229,96 @@ def workload_name(args):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def _time_ms(fn, reps, warm=2):
+    for _ in range(warm):
+        fn()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def run_cfg4(args):
+    """BASELINE configs[3]: one keyframe + 4 frames at 640x480, K=128, 10 LM iterations per level, as nb=4 independent pairs (the reference has no
+    joint multi-view solve): the dense 4-level variant and the sparse N=4096 variant of legacy/seq_example.py:12 (3C layout, ragged)."""
+    from banet_b200 import ops, synth, _lib
+    _lib.require_device()
+    dev = torch.device("cuda", 0)
+    C, K, nb, iters = args.channels, 128, 4, 10
+    peak, peak_kind = measured_peaks()
+    out = []
+    for variant, npts in (("dense", None), ("sparse4096", 4096)):
+        sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 4, device=dev, dtype=torch.float32, n_points=npts)
+        lay_f2 = npts is None
+        levels = [ops.Level(l.conv1, l.conv2[..., :C].contiguous() if lay_f2 else l.conv2, l.intr, l.p, l.D, l.B, grid=l.grid) for l in sc.levels]
+        g = torch.Generator().manual_seed(7)
+        dims = [C, 2 * C, 4 * C, 2 * C, C, 1]
+        packed = [ops.pack_mlp([(torch.randn(dims[i], dims[i + 1], generator=g) * (2.0 / dims[i]) ** 0.5, torch.zeros(dims[i + 1])) for i in range(5)]).to(dev) for _ in LEVEL_IDS]
+        ws = torch.empty(ops.lm_run_workspace_bytes(levels, _lib.PREC_AUTO), dtype=torch.uint8, device=dev)
+        ms = _time_ms(lambda: ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws), max(3, args.steps))
+        N_tot = sum(l.N for l in sc.levels)
+        # sparse points: no texel reuse, every point reads its own 4 taps of the 3C map
+        by = nb * iters * sum((4 * l.N * (2 * C + K + 4) if npts is None else 4 * l.N * (C + 12 * C + K + 4)) + 4 * ((6 + K) ** 2 + 6 + K + C) for l in sc.levels)
+        out.append({"variant": variant, "points_per_pair_sum_levels": N_tot, "ms_per_solve": ms, "pair_iters_per_s": nb * len(levels) * iters / (ms * 1e-3),
+                    "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak,
+                    "launches_per_solve": 1 + len(levels) * iters * 3})
+        del sc, levels
+        torch.cuda.empty_cache()
+    print(json.dumps({"metric": METRIC, "unit": UNIT, "value": out[0]["pair_iters_per_s"], "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+                      "config": {"workload": "cfg4: keyframe + 4 frames as nb=4 pairs, 640x480 4-level pyramid, K=128, 10 LM iters/level; dense (F2-only layout, "
+                                             "generation-7 kernel) and sparse N=4096 random sub-pixel points per level ([F2|gx|gy] layout, ragged tiles)", "precision": "auto"},
+                      "variants": out, "roofline": {"bound": "hbm (dense) / launch+latency (sparse)", "peak": peak, "peak_kind": peak_kind, "unit": "GB/s"}}))
+
+
+def run_cfg5(args):
+    """BASELINE configs[4]: depth-basis sweep K in {32,64,128,256} at 640x480 (one level), nb=64, 5 LM iterations: H_dd on tensor cores
+    (tcgen05 kind::tf32, AUTO policy) vs the fp32 SIMT register-tiled path."""
+    from banet_b200 import ops, synth, _lib
+    _lib.require_device()
+    dev = torch.device("cuda", 0)
+    C, nb, iters = args.channels, args.nb if args.nb != 32 else 64, 5
+    peak, peak_kind = measured_peaks()
+    sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=256, level_ids=(3,), seed=1234 + 5, device=dev, dtype=torch.float32)
+    l = sc.levels[0]
+    f2 = l.conv2[..., :C].contiguous()
+    l.conv2 = None
+    torch.cuda.empty_cache()
+    sweep = []
+    for K in (32, 64, 128, 256):
+        B = l.B[..., :K].contiguous(); W0 = sc.W0[:, :K].contiguous()
+        lv = [ops.Level(l.conv1, f2, l.intr, l.p, l.D, B, grid=l.grid)]
+        row = {"K": K}
+        for name, prec in (("tensor_core", _lib.PREC_AUTO), ("fp32_simt", _lib.PREC_FP32_SIMT)):
+            if name == "tensor_core" and K == 256:
+                row[name] = None                   # K = 256 runs on the SIMT path only (no tensor-core instantiation: 2 x 272 TMEM columns > 512)
+                continue
+            reps = 2 if (name == "fp32_simt" and K >= 128) else 3
+            ms_b = _time_ms(lambda: ops.lm_build(lv[0], sc.R0, sc.T0, W0, precision=prec), reps, warm=1)
+            ms_s = _time_ms(lambda: ops.lm_run(lv, iters, sc.R0, sc.T0, W0, lambda_fixed=0.05, precision=prec), reps, warm=1)
+            by = nb * algorithmic_bytes_per_pair_iter(l.N, C, K)
+            row[name] = {"build_ms": ms_b, "solve_ms_5_iters": ms_s, "pair_iters_per_s": nb * iters / (ms_s * 1e-3), "build_gbs": by / (ms_b * 1e-3) / 1e9,
+                         "build_frac_of_hbm_peak": by / (ms_b * 1e-3) / 1e9 / peak, "build_tflops": nb * 2.0 * l.N * K * (K + 7) / (ms_b * 1e-3) / 1e12}
+        sweep.append(row)
+        del B, lv
+        torch.cuda.empty_cache()
+    best = max(r["tensor_core"]["pair_iters_per_s"] for r in sweep if r["K"] == 128 and r["tensor_core"])
+    print(json.dumps({"metric": METRIC, "unit": UNIT, "value": best, "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
+                      "config": {"workload": f"cfg5: K sweep at 640x480 (one dense level), nb={nb}, C={C}, 5 LM iters, fixed lambda; F2-only layout", "precision": "auto vs fp32"},
+                      "sweep": sweep, "roofline": {"bound": "hbm", "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                                                   "alg_bytes_per_pair_iter": "4*N*(2C+K+4) + 4*(P^2+P+C)", "tensor_flops_per_pair_iter": "2*N*K*(K+7)"}}))
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.config == "cfg4":
+        return run_cfg4(args)
+    if args.config == "cfg5":
+        return run_cfg5(args)
 
     from banet_b200 import ops, synth, _lib
     from banet_b200 import dist as bdist

@@ -107,7 +107,7 @@ typedef struct banet_level {
                                  8x8 tiles so that every conv2 texel is fetched from HBM about once */
 } banet_level_t;
 
-#define BANET_PREC_AUTO    (-1)   /* TF32X2 where the tensor-core path applies (K=128, C in {64,128}), else FP32_SIMT */
+#define BANET_PREC_AUTO    (-1)   /* the level-wise policy (TF32_LEVELWISE) where the tensor-core path applies (K in {32,64,128}, C in {64,128}), else FP32_SIMT */
 #define BANET_PREC_FP32_SIMT 0   /* every contraction in fp32 FFMA (reference-exact arithmetic type)   */
 #define BANET_PREC_TF32X1    1   /* B^T diag(s) B on tcgen05 kind::tf32: basis truncated by the tensor core, s*b rounded to nearest */
 #define BANET_PREC_TF32X2    2   /* split-A two-pass tf32: b = trunc(b) + (b - trunc(b)); only s*b's rounding remains             */

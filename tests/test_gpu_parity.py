@@ -90,7 +90,7 @@ def test_pre_steps_match_oracle():
 # ---------------------------------------------------------------------------------------------- build
 @pytest.mark.parametrize("C,K,n_points,fly", [
     (8, 4, None, False), (8, 0, None, False), (128, 128, None, False), (6, 5, 333, False), (5, 16, 100, False),
-    (12, 32, None, True), (16, 64, 1000, False), (128, 16, None, True)])
+    (12, 32, None, True), (16, 64, 1000, False), (128, 16, None, True), (16, 256, 700, False), (8, 200, None, False)])
 def test_lm_build_matches_oracle(C, K, n_points, fly):
     ops = _ops()
     sc = scene_case(nb=3, H=24 if C == 128 else 48, W=32 if C == 128 else 64, C=C, K=K, level_ids=(3,), seed=7 + C + K,
