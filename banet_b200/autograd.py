@@ -114,6 +114,7 @@ def iteration(conv1, conv2, intr, p, D, B, R, T, W, mlp_params, l2_regularizer_b
     if bundle:
         jd = torch.stack([fx * ((Rp[:, 0] - Rp[:, 2] * x) * iZ), fy * ((Rp[:, 1] - Rp[:, 2] * y) * iZ)], dim=2)   # :63-74
         J = torch.cat([J, jd.unsqueeze(-1) * B.unsqueeze(-2)], dim=-1)            # :260-261
+    J = torch.where(ok.unsqueeze(-1).unsqueeze(-1), J, torch.zeros_like(J))        # masked / non-finite projections: no 0 * inf (the fused kernels skip them)
     AtA, Atb = ops.equation_construction(J.contiguous(), grad.contiguous(), diff.contiguous(), exact_sym)   # :263 (native fwd + bwd)
     diag = torch.diagonal(AtA, dim1=-2, dim2=-1)
     if bundle:

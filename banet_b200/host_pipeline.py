@@ -49,7 +49,10 @@ class HostSolver:
         for hl in self.host:
             d = {}
             for name in _NAMES:
-                t = hl[name]
+                t = hl.get(name)
+                if t is None:                     # pose-only levels carry no basis
+                    d[name] = None
+                    continue
                 d[name] = torch.empty(t.shape, dtype=torch.float32, device=self.dev)
                 self.h2d_bytes += t.numel() * 4
             if self.derive:                       # staging of the feature maps; conv2 on the device is the 3C tensor
@@ -60,7 +63,7 @@ class HostSolver:
         self._ws: Optional[Tensor] = None
 
     def _levels(self, a: int, b: int) -> List[ops.Level]:
-        return [ops.Level(d["conv1"][a:b], d["conv2"][a:b], d["intr"][a:b], d["p"][a:b], d["D"][a:b], d["B"][a:b], grid=hl.get("grid"))
+        return [ops.Level(d["conv1"][a:b], d["conv2"][a:b], d["intr"][a:b], d["p"][a:b], d["D"][a:b], None if d["B"] is None else d["B"][a:b], grid=hl.get("grid"))
                 for d, hl in zip(self.dev_levels, self.host)]
 
     def solve(self, R0: Tensor, T0: Tensor, W0: Tensor, iters_per_level: int, mlp_packed=None, l2_regularizer_base: float = 1000.0,
@@ -68,9 +71,10 @@ class HostSolver:
         """R0 [nb,3,3], T0 [nb,3,1], W0 [nb,K,1] on the host (pinned for async copies).  Returns device (R, T, W, status); when
         `out` = three host tensors is given they receive the results too (device->host inside the pipeline)."""
         nb, dev = self.nb, self.dev
-        R = torch.empty(nb, 3, 3, device=dev); T = torch.empty(nb, 3, 1, device=dev); W = torch.empty(W0.shape, device=dev)
+        R = torch.empty(nb, 3, 3, device=dev); T = torch.empty(nb, 3, 1, device=dev)
+        W = None if W0 is None else torch.empty(W0.shape, device=dev)
         status = torch.empty(nb, dtype=torch.int32, device=dev)
-        dR = torch.empty_like(R); dT = torch.empty_like(T); dW = torch.empty_like(W)
+        dR = torch.empty_like(R); dT = torch.empty_like(T); dW = None if W is None else torch.empty_like(W)
         self.copy_stream.wait_stream(torch.cuda.current_stream(dev))
         self.compute_stream.wait_stream(torch.cuda.current_stream(dev))
         events = []
@@ -79,8 +83,9 @@ class HostSolver:
                 for d, hl in zip(self.dev_levels, self.host):
                     for name in _NAMES:
                         dst = d["feat"] if (name == "conv2" and self.derive) else d[name]
-                        dst[a:b].copy_(hl[name][a:b], non_blocking=True)
-                dR[a:b].copy_(R0[a:b], non_blocking=True); dT[a:b].copy_(T0[a:b], non_blocking=True); dW[a:b].copy_(W0[a:b], non_blocking=True)
+                        if dst is not None:
+                            dst[a:b].copy_(hl[name][a:b], non_blocking=True)
+                dR[a:b].copy_(R0[a:b], non_blocking=True); dT[a:b].copy_(T0[a:b], non_blocking=True); (dW is not None) and dW[a:b].copy_(W0[a:b], non_blocking=True)
                 ev = torch.cuda.Event(); ev.record(self.copy_stream); events.append(ev)
         with torch.cuda.stream(self.compute_stream):
             for (a, b), ev in zip(self.ranges, events):
@@ -91,15 +96,20 @@ class HostSolver:
                 lv = self._levels(a, b)
                 if self._ws is None:
                     self._ws = torch.empty(ops.lm_run_workspace_bytes(lv, self.precision), dtype=torch.uint8, device=dev)
-                r, t, w, st = ops.lm_run(lv, iters_per_level, dR[a:b], dT[a:b], dW[a:b], mlp_packed=mlp_packed,
+                r, t, w, st = ops.lm_run(lv, iters_per_level, dR[a:b], dT[a:b], None if dW is None else dW[a:b], mlp_packed=mlp_packed,
                                          l2_regularizer_base=l2_regularizer_base, lambda_fixed=lambda_fixed, workspace=self._ws,
                                          precision=self.precision)
-                R[a:b] = r; T[a:b] = t; W[a:b] = w; status[a:b] = st
+                R[a:b] = r; T[a:b] = t; status[a:b] = st
+                if W is not None:
+                    W[a:b] = w
                 if out is not None:
-                    out[0][a:b].copy_(r, non_blocking=True); out[1][a:b].copy_(t, non_blocking=True); out[2][a:b].copy_(w, non_blocking=True)
+                    out[0][a:b].copy_(r, non_blocking=True); out[1][a:b].copy_(t, non_blocking=True)
+                    if W is not None:
+                        out[2][a:b].copy_(w, non_blocking=True)
         torch.cuda.current_stream(dev).wait_stream(self.compute_stream)
         for t_ in (R, T, W, status, dR, dT, dW):
-            t_.record_stream(self.compute_stream)
+            if t_ is not None:
+                t_.record_stream(self.compute_stream)
         return R, T, W, status
 
 

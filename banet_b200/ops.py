@@ -203,11 +203,13 @@ def lm_lambda(rbar_sum: Tensor, N: int, mlp_packed: Tensor, base: float) -> Tens
 
 
 def lm_solve_update(H: Tensor, g: Tensor, lam: Tensor, R: Tensor, T: Tensor, W: Optional[Tensor],
-                    damping_eps: float = 1e-5, undamped_last: bool = True, vmatrix_batch_scramble: bool = False):
-    """-> R', T', W', delta [nb,P], status [nb] (int32)."""
+                    damping_eps: float = 1e-5, undamped_last: Optional[bool] = None, vmatrix_batch_scramble: bool = False):
+    """-> R', T', W', delta [nb,P], status [nb] (int32).  undamped_last None: True for K > 0 (bundlenet.py:266), False for pose-only (:182)."""
     lib = load()
     Hc = _chk(H, "H"); nb, P, _ = Hc.shape
     K = P - 6
+    if undamped_last is None:
+        undamped_last = K > 0
     gc = _chk(g.reshape(nb, P), "g", (nb, P)); lc = _chk(lam.reshape(nb), "lambda", (nb,))
     R = _chk(R, "R", (nb, 3, 3)); T = _chk(T, "T", (nb, 3, 1))
     Wt = None if K == 0 else _chk(W, "W", (nb, K, 1))
@@ -246,7 +248,7 @@ def lm_step(H: Tensor, g: Tensor, rbar_sum: Optional[Tensor], N: int, mlp_packed
 
 
 def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
-           mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: float = 1000.0,
+           mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: Optional[float] = None,
            lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,
            vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_AUTO, workspace: Optional[Tensor] = None):
     """Whole coarse-to-fine solve on the device (banet_lm_run).  Returns new (R,T,W,status); inputs are not modified."""
@@ -260,6 +262,8 @@ def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, 
     Wt = None if K == 0 else _chk(W, "W", (nb, K, 1)).clone()
     if undamped_last is None:
         undamped_last = K > 0
+    if l2_regularizer_base is None:              # BundleIteration scales lambda by 1000 (bundlenet.py:252-253, 393); CameraIteration ignores the base (:165-173)
+        l2_regularizer_base = 1000.0 if K > 0 else 1.0
     mlp_ptrs = (C.c_void_p * len(structs))()
     have = False
     for i in range(len(structs)):

@@ -11,7 +11,7 @@ Every function cites the reference lines it follows (paths relative to
     R  [nb,3,3]  T [nb,3,1]
 
 Everything is torch-CPU and differentiable, so the same code is also the
-gradient oracle (float64).  PARITY UNPINNED: see oracle/__init__.py.
+gradient oracle (float64).  Pinned to the reference's own code: see oracle/__init__.py.
 """
 from __future__ import annotations
 
@@ -371,7 +371,7 @@ def normal_equations_structured(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W,
         H_cc = sum Jc^T M Jc      g_c = sum Jc^T q
         H_cd = sum (Jc^T M jd) b^T               g_d = sum (jd^T q) b
         H_dd = sum (jd^T M jd) b b^T
-    Used only to prove the decomposition exact (tests/test_oracle_structured.py).
+    Used to prove the decomposition exact (tests/test_oracle_consistency.py) and as the checker at BASELINE sizes.
     B is None -> pose-only (P=6).
     """
     nb, N, C = conv1.shape
