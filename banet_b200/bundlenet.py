@@ -206,3 +206,40 @@ class BundleNet(torch.nn.Module):
             depth = compose(init_depth.reshape(nb, -1), basis.reshape(nb, -1, K), W)   # :397
             Ds.append(depth.reshape(nb, oh, ow, 1))
         return Rs, Ts, Ds
+
+    # ---- training losses (reference bundlenet.py:401-463): stock torch, like the CNN around the layer ---------------------------------
+    def lossR(self, predQ: Tensor, gtQ: Tensor) -> Tensor:
+        """bundlenet.py:401-404: tf.losses.cosine_distance of unit quaternions = mean(1 - <pred, gt>)."""
+        return (1.0 - (predQ * gtQ).sum(dim=1, keepdim=True)).mean()
+
+    def lossT(self, predT: Tensor, gtT: Tensor) -> Tensor:
+        """bundlenet.py:411-413 (the second definition, which overrides the angular one of :406-409): mean |predT - gtT|."""
+        return (predT - gtT).abs().mean()
+
+    def lossF(self, intrisic: Tensor, depth: Tensor, mask: Tensor, predR: Tensor, predT: Tensor, gtR: Tensor, gtT: Tensor) -> Tensor:
+        """bundlenet.py:415-463: masked mean |flow(pred) - flow(gt)| over the dense pixel grid in units of the image width, times total / valid."""
+        geo = self.geo
+        nb, h, w = depth.shape[0], depth.shape[1], depth.shape[2]
+        npix = h * w
+        k = intrisic.reshape(nb, 4)
+        fx = (geo.fx_num * k[:, 0:1] / geo.fx_den); fy = (geo.fy_num * k[:, 1:2] / geo.fy_den)
+        ox = geo.fx_num * k[:, 2:3] / geo.fx_den - geo.ox_sub; oy = geo.fy_num * k[:, 3:4] / geo.fy_den - geo.oy_sub
+        yy, xx = torch.meshgrid(torch.arange(h, device=depth.device, dtype=depth.dtype), torch.arange(w, device=depth.device, dtype=depth.dtype), indexing="ij")
+        ray = torch.stack([(xx.reshape(1, -1) - ox) / fx, (yy.reshape(1, -1) - oy) / fy, torch.ones(nb, npix, device=depth.device, dtype=depth.dtype)], dim=1)
+        p = ray * torch.rsqrt(torch.clamp((ray * ray).sum(dim=1, keepdim=True), min=1e-12))
+        m = mask.reshape(nb, npix)
+
+        def flow(Rm, Tm):
+            X = (Rm @ p) * depth.reshape(nb, 1, npix) + Tm.reshape(nb, 3, 1)
+            return fx * (X[:, 0] / X[:, 2]) + ox, fy * (X[:, 1] / X[:, 2]) + oy
+
+        fxp, fyp = flow(predR, predT); fxg, fyg = flow(gtR, gtT)
+        return (float(npix * nb) / m.sum()) * (((fxp - fxg).abs() * m).mean() / w + ((fyp - fyg).abs() * m).mean() / w)
+
+
+def rotation2quaternion(R: Tensor, name=None) -> Tensor:
+    """reference bundlenet.py:6-15: [nb,3,3] -> unit quaternion [nb,4] (w first)."""
+    diag = 1.0 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    q0 = torch.sqrt(diag) / 2.0
+    q = torch.stack([q0, (R[:, 2, 1] - R[:, 1, 2]) / (4.0 * q0), (R[:, 0, 2] - R[:, 2, 0]) / (4.0 * q0), (R[:, 1, 0] - R[:, 0, 1]) / (4.0 * q0)], dim=1)
+    return q * torch.rsqrt(torch.clamp((q * q).sum(dim=1, keepdim=True), min=1e-12))

@@ -683,3 +683,46 @@ def legacy_track(intrisic, layers, points, d, initR, initT, level_iters, mlp_par
     if not early_termination:
         return rotations[1:], translations[1:], ratio
     return R, T, ratio
+
+
+# --------------------------------------------------------------------------- training losses (bundlenet.py:6-15, 401-463)
+def rotation2quaternion(R: Tensor) -> Tensor:
+    """bundlenet.py:6-15 `rotation2quaternion`: [nb,3,3] -> unit quaternion [nb,4] (w first; assumes 1 + trace > 0)."""
+    diag = 1.0 + R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    q0 = torch.sqrt(diag) / 2.0
+    q = torch.stack([q0, (R[:, 2, 1] - R[:, 1, 2]) / (4.0 * q0), (R[:, 0, 2] - R[:, 2, 0]) / (4.0 * q0), (R[:, 1, 0] - R[:, 0, 1]) / (4.0 * q0)], dim=1)
+    return q / torch.sqrt(torch.clamp((q * q).sum(dim=1, keepdim=True), min=1e-12))
+
+
+def loss_r(predQ: Tensor, gtQ: Tensor) -> Tensor:
+    """bundlenet.py:401-404 `lossR`: tf.losses.cosine_distance of quaternions = mean(1 - <pred, gt>)."""
+    return (1.0 - (predQ * gtQ).sum(dim=1, keepdim=True)).mean()
+
+
+def loss_t(predT: Tensor, gtT: Tensor) -> Tensor:
+    """bundlenet.py:411-413 (the second `lossT` definition overrides the angular one at :406-409): mean |predT - gtT|."""
+    return (predT - gtT).abs().mean()
+
+
+def loss_f(intrisic: Tensor, depth: Tensor, mask: Tensor, predR: Tensor, predT: Tensor, gtR: Tensor, gtT: Tensor,
+           geo: ResizeGeometry = ResizeGeometry()) -> Tensor:
+    """bundlenet.py:415-463 `lossF`: mean masked |flow(pred) - flow(gt)| of the dense pixel grid, in units of the image width, rescaled by
+    total / valid.  intrisic [nb,4,1], depth [nb,h,w,1], mask [nb,h,w,1], R [nb,3,3], T [nb,3]."""
+    nb, h, w = depth.shape[0], depth.shape[1], depth.shape[2]
+    npix = h * w
+    predT, gtT = predT.unsqueeze(-1), gtT.unsqueeze(-1)
+    m = mask.reshape(nb, npix)
+    fx = geo.fx_num * intrisic[:, 0].repeat(1, npix) / geo.fx_den
+    fy = geo.fy_num * intrisic[:, 1].repeat(1, npix) / geo.fy_den
+    ox = geo.fx_num * intrisic[:, 2].repeat(1, npix) / geo.fx_den - geo.ox_sub
+    oy = geo.fy_num * intrisic[:, 3].repeat(1, npix) / geo.fy_den - geo.oy_sub
+    yy, xx = torch.meshgrid(torch.arange(h, dtype=depth.dtype), torch.arange(w, dtype=depth.dtype), indexing="ij")
+    pts = torch.stack([xx.reshape(-1), yy.reshape(-1)], dim=-1).unsqueeze(0).repeat(nb, 1, 1)
+    p = compute_coordinates(pts, fx, fy, ox, oy)
+
+    def flow(Rm, Tm):
+        X = (Rm @ p) * depth.reshape(nb, 1, npix) + Tm
+        return fx * (X[:, 0] / X[:, 2]) + ox, fy * (X[:, 1] / X[:, 2]) + oy
+
+    fxp, fyp = flow(predR, predT); fxg, fyg = flow(gtR, gtT)
+    return (float(npix * nb) / m.sum()) * (((fxp - fxg).abs() * m).mean() / w + ((fyp - fyg).abs() * m).mean() / w)

@@ -119,7 +119,7 @@ def _shape_list(shape):
 
 _tf.zeros = lambda shape, dtype=None, name=None: torch.zeros(_shape_list(shape), dtype=_dtype(dtype))
 _tf.ones = lambda shape, dtype=None, name=None: torch.ones(_shape_list(shape), dtype=_dtype(dtype))
-_tf.range = lambda n, name=None: torch.arange(int(n), dtype=torch.int64)
+_tf.range = lambda a, b=None, name=None: torch.arange(int(a), dtype=torch.int64) if b is None else torch.arange(int(a), int(b), dtype=torch.int64)
 _tf.reshape = lambda x, shape, name=None: x.reshape(_shape_list(shape))
 _tf.transpose = lambda x, perm=None, name=None: x.permute(*perm) if perm is not None else x.t()
 _tf.expand_dims = lambda x, axis=None, name=None, dim=None: x.unsqueeze(axis if axis is not None else dim)
@@ -296,7 +296,13 @@ def _resampler(data, warp, name=None):
 
 
 _tf.contrib = types.SimpleNamespace(resampler=types.SimpleNamespace(resampler=_resampler))
-_tf.losses = types.SimpleNamespace()
+def _cosine_distance(labels, predictions, axis=None, weights=1.0, scope=None, dim=None, **kw):
+    """tf.losses.cosine_distance (TF 1.x): losses = 1 - sum(labels * predictions, axis, keepdims); default reduction SUM_BY_NONZERO_WEIGHTS = mean."""
+    axis = axis if axis is not None else dim
+    return (1.0 - (labels * predictions).sum(dim=axis, keepdim=True)).mean()
+
+
+_tf.losses = types.SimpleNamespace(cosine_distance=_cosine_distance)
 _tf.train = types.SimpleNamespace()
 
 

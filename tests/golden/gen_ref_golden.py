@@ -111,6 +111,25 @@ def case_resize(bn):
     return out
 
 
+def loss_inputs(seed=27, nb=2, h=12, w=16):
+    g = torch.Generator().manual_seed(seed)
+    Rp = GG.synth.rodrigues(torch.randn(nb, 3, generator=g) * 0.05).to(F64); Rg = GG.synth.rodrigues(torch.randn(nb, 3, generator=g) * 0.05).to(F64)
+    Tp = torch.randn(nb, 3, generator=g, dtype=F64) * 0.1; Tg = torch.randn(nb, 3, generator=g, dtype=F64) * 0.1
+    depth = 1.0 + 2.0 * torch.rand(nb, h, w, 1, generator=g, dtype=F64)
+    mask = (torch.rand(nb, h, w, 1, generator=g) > 0.3).to(F64)
+    intr = torch.tensor([[[20.0], [21.0], [8.0], [6.0]]], dtype=F64).repeat(nb, 1, 1)
+    return dict(Rp=Rp, Rg=Rg, Tp=Tp, Tg=Tg, depth=depth, mask=mask, intr=intr)
+
+
+def case_losses(bn):
+    """rotation2quaternion (bundlenet.py:6-15), lossR / lossT / lossF (:401-463)."""
+    x = loss_inputs()
+    net = bn.BundleNet()
+    qp, qg = bn.rotation2quaternion(x["Rp"]), bn.rotation2quaternion(x["Rg"])
+    return dict(out_qp=_np(qp), out_qg=_np(qg), out_lossR=np.array([float(net.lossR(qp, qg))]), out_lossT=np.array([float(net.lossT(x["Tp"], x["Tg"]))]),
+                out_lossF=np.array([float(net.lossF(x["intr"], x["depth"], x["mask"], x["Rp"], x["Tp"], x["Rg"], x["Tg"]))]))
+
+
 def legacy_inputs():
     """One keyframe->frame pair for the legacy pose-only tracker (legacy/ba.py; nb = 1 there): sparse points, C=6."""
     sc = GG._scene(1, 48, 64, 6, 0, (3,), 25, n_points=400)
@@ -184,7 +203,7 @@ if __name__ == "__main__":
     cases = {"ref_primitives": case_primitives(bn, ba, up),
              "ref_bundle_iteration_nb1": case_bundle_iteration(bn, 1), "ref_bundle_iteration_nb2": case_bundle_iteration(bn, 2),
              "ref_camera_iteration_nb1": case_camera_iteration(bn, 1), "ref_camera_iteration_nb2": case_camera_iteration(bn, 2),
-             "ref_resize": case_resize(bn), "ref_legacy": case_legacy(ba), "ref_track": case_track(ba)}
+             "ref_resize": case_resize(bn), "ref_legacy": case_legacy(ba), "ref_track": case_track(ba), "ref_losses": case_losses(bn)}
     for name, out in cases.items():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})

@@ -134,3 +134,15 @@ def test_legacy_tracker_loop_matches_reference_code():
     assert rel_fro(R, r["out_early_R"]) < TOL and float((T - _t(r["out_early_T"])).abs().max()) < 1e-13 and abs(float(ratio) - float(r["out_early_ratio"][0])) < 1e-9
     Rs, Ts, ratio = O.legacy_track(x["intr"], x["layers"], x["points"], x["d"], x["R0"], x["T0"], [2, 2, 2], mlps, early_termination=False)
     assert rel_fro(torch.stack(Rs), r["out_fixed_R"]) < TOL and float((torch.stack(Ts) - _t(r["out_fixed_T"])).abs().max()) < 1e-13
+
+
+def test_losses_match_reference_code():
+    """rotation2quaternion, lossR, lossT (the overriding mean-abs definition), lossF executed from bundlenet.py:6-15, 401-463."""
+    import gen_ref_golden as GR
+    r = _ref("ref_losses")
+    x = GR.loss_inputs()
+    qp, qg = O.rotation2quaternion(x["Rp"]), O.rotation2quaternion(x["Rg"])
+    assert rel_fro(qp, r["out_qp"]) < TOL and rel_fro(qg, r["out_qg"]) < TOL
+    assert abs(float(O.loss_r(qp, qg)) - float(r["out_lossR"][0])) < 1e-12
+    assert abs(float(O.loss_t(x["Tp"], x["Tg"])) - float(r["out_lossT"][0])) < 1e-12
+    assert abs(float(O.loss_f(x["intr"], x["depth"], x["mask"], x["Rp"], x["Tp"], x["Rg"], x["Tg"])) - float(r["out_lossF"][0])) < 1e-10 * max(1.0, float(r["out_lossF"][0]))
