@@ -39,7 +39,7 @@ constexpr int CHAIN = 8, TMEM_COLS = 512, ACCL = 320;
 #define BANET_TC7_WY 13
 #endif
 #ifndef BANET_TC7_NWB
-#define BANET_TC7_NWB 3
+#define BANET_TC7_NWB 2
 #endif
 #ifndef BANET_TC7_NST1
 #define BANET_TC7_NST1 3
@@ -53,6 +53,8 @@ constexpr int BOX_Y = BANET_TC7_DBG_BOXY;
 constexpr int BOX_Y = WY;
 #endif
 constexpr int WIN_TX_BYTES = WX * BOX_Y * CHK * 4;
+constexpr int C1_BYTES = TILE * CHK * 4;                        // conv1 chunk of the tile: [8][8] pixels x 32 channels, pixel-major 128-B rows
+constexpr int WBUF = WIN_BYTES + C1_BYTES;                      // one ring buffer = F2 window chunk + conv1 chunk
 
 template <int MODE, int NCH> struct Smem {
     static_assert(MODE == 1 || MODE == 2, "generation 7 implements TF32X1 and TF32X2 (TF32X3 stays on generation 6: no room for the windows)");
@@ -65,8 +67,8 @@ template <int MODE, int NCH> struct Smem {
     static constexpr int off_R = NST * STAGE_A;
     static constexpr int off_Alo = off_R + STAGE_R;
     static constexpr int off_Rlo = off_Alo + (MODE >= 2 ? STAGE_A : 0);      // (MODE 3 only; kept so that the shared algebra code compiles)
-    static constexpr int off_win = off_Rlo;                            // [NWB][WY][WX][32] floats
-    static constexpr int off_misc = off_win + NWB * WIN_BYTES;
+    static constexpr int off_win = off_Rlo;                            // [NWB] x ([WY][WX][32] floats F2 window chunk | [64][32] floats conv1 chunk)
+    static constexpr int off_misc = off_win + NWB * WBUF;
     static constexpr int off_bar = off_misc;                           // 22 + 2*NWB mbarriers (<= 30)
     static constexpr int off_tmem = off_bar + 30 * 8;
     static constexpr int off_tile = off_misc + 256;                    // [NREC][4] ints: pair index of the tile in record buffer s
@@ -91,6 +93,23 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr));
     return r;
 }
+// packed fp32 pairs (sm_100: FFMA2 / FMUL2 / FADD2, one issue slot for two lanes' worth of channels; a (w, w) pair is encoded as a scalar broadcast)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float2 upk2(u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ ulonglong2 lds2x64(uint32_t saddr) {
+    ulonglong2 r;
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(saddr));
+    return r;
+}
+__device__ __forceinline__ ulonglong2 ldg2x64(const float* p) {
+    ulonglong2 r;
+    asm volatile("ld.global.nc.v2.b64 {%0,%1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float qsum8(float v) {               // sum over the 8 lanes of a quarter-warp
     v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 1);
     return v;
@@ -110,9 +129,30 @@ __device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long lon
     return tc;
 }
 
+// incremental form of tile_coord (no integer divisions per tile): walks the same band order
+struct TileStepper {
+    int b, r, band, txi, tyr, rows;              // pair, tile index inside the pair, band, tile column, row inside the band, rows of the band
+    __device__ __forceinline__ void init(const BuildParams& prm, long long tl) {
+        const unsigned t = (unsigned)tl, tpp = (unsigned)prm.tiles_per_pair;
+        b = (int)(t / tpp); r = (int)(t - (unsigned)b * tpp);
+        const int bandsz = prm.tiles_x * prm.band_rows;
+        band = r / bandsz;
+        const int rem = r - band * bandsz;
+        rows = min(prm.band_rows, prm.tiles_y - band * prm.band_rows);
+        txi = rem / rows; tyr = rem - txi * rows;
+    }
+    __device__ __forceinline__ int tx0() const { return txi * 8; }
+    __device__ __forceinline__ int ty0(const BuildParams& prm) const { return (band * prm.band_rows + tyr) * 8; }
+    __device__ __forceinline__ void next(const BuildParams& prm) {
+        if (++r == prm.tiles_per_pair) { r = 0; ++b; band = 0; txi = 0; tyr = 0; rows = min(prm.band_rows, prm.tiles_y); return; }
+        if (++tyr == rows) { tyr = 0; if (++txi == prm.tiles_x) { txi = 0; ++band; rows = min(prm.band_rows, prm.tiles_y - band * prm.band_rows); } }
+    }
+};
+
 template <int NCH, int MODE, int KBLK = 4>
 __global__ void __launch_bounds__(THREADS, 1)
-lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapF, const BuildParams prm)
+lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_constant__ CUtensorMap tmapF, const __grid_constant__ CUtensorMap tmapC,
+                    const BuildParams prm)
 {
     using SM = Smem<MODE, NCH>;
     constexpr int NST = SM::NST, NREC = SM::NREC, NWB = SM::NWB;
@@ -160,7 +200,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         mbar_init(&chain_done[0], 1); mbar_init(&chain_done[1], 1); mbar_init(&drained[0], DW); mbar_init(&drained[1], DW);
         mbar_init(rbdump, GW); mbar_init(rbfree, AW);
         fence_barrier_init();
-        prefetch_tmap(&tmapB); prefetch_tmap(&tmapF);
+        prefetch_tmap(&tmapB); prefetch_tmap(&tmapF); prefetch_tmap(&tmapC);
     }
     if (warp == 0) tmem_alloc<TMEM_COLS>(s_tmem);
     for (int i = tid; i < TILE * 8; i += THREADS) {       // pad chunks of R's 5th block stay zero
@@ -185,26 +225,31 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         float* myW = sW + gwi * 128;
         int geom_b = -1;
         uint32_t dseed = 0;                                  // MODE 1: dither seed of the current pair
+        TileStepper cur, ahead;
+        cur.init(prm, t_begin);
+        ahead.init(prm, t_begin); ahead.next(prm); ahead.next(prm);
         for (int j = 0; j < ntiles; ++j) {
-            const TileCoord tc = tile_coord(prm, t_begin + j);
+            TileCoord tc; tc.b = cur.b; tc.tx0 = cur.tx0(); tc.ty0 = cur.ty0(prm); tc.n0 = 0; tc.cnt = TILE;
+            cur.next(prm);
             const int b = tc.b;
             if (gwi == 1 && j + 2 < ntiles) {             // L2 prefetch of the streaming inputs (conv1, p, D) two tiles ahead
-                const TileCoord tn = tile_coord(prm, t_begin + j + 2);
+                const int atx = ahead.tx0(), aty = ahead.ty0(prm), ab = ahead.b;
                 if (lane < 8) {
-                    const int gy = tn.ty0 + lane;
-                    if (gy < prm.grid_h && tn.tx0 < prm.grid_w) {
-                        const size_t n = (size_t)gy * prm.grid_w + tn.tx0;
-                        const int wpx = min(8, prm.grid_w - tn.tx0);
-                        prefetch_l2_bulk(prm.conv1 + ((size_t)tn.b * N + n) * C, (uint32_t)(wpx * C * 4));
+                    const int gy = aty + lane;
+                    if (gy < prm.grid_h && atx < prm.grid_w) {
+                        const size_t n = (size_t)gy * prm.grid_w + atx;
+                        const int wpx = min(8, prm.grid_w - atx);
+                        prefetch_l2_bulk(prm.conv1 + ((size_t)ab * N + n) * C, (uint32_t)(wpx * C * 4));
                         if ((n & 3) == 0 && (N & 3) == 0) {
                             const uint32_t by = (uint32_t)(((wpx * 4) + 15) & ~15);
-                            prefetch_l2_bulk(prm.D + (size_t)tn.b * N + n, by);
+                            prefetch_l2_bulk(prm.D + (size_t)ab * N + n, by);
 #pragma unroll
-                            for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)tn.b * 3 + k) * N + n, by);
+                            for (int k = 0; k < 3; ++k) prefetch_l2_bulk(prm.p + ((size_t)ab * 3 + k) * N + n, by);
                         }
                     }
                 }
             }
+            ahead.next(prm);
             if (b != geom_b) {
                 geom_b = b;
                 __syncwarp();
@@ -296,7 +341,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             bymin = __reduce_min_sync(0xffffffffu, bymin); bymax = __reduce_max_sync(0xffffffffu, bymax);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(sBox + (sr * W0 + gwi) * 4) = make_int4(bxmin, bxmax, bymin, bymax);
-                if (gwi == 0) sTile[sr * 4] = b;
+                if (gwi == 0) { sTile[sr * 4] = b; sTile[sr * 4 + 1] = tc.tx0; sTile[sr * 4 + 2] = tc.ty0; }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&recs[sr]);
@@ -307,34 +352,27 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         const int g = warp - W0, pq = lane >> 3, ql = lane & 7;          // quarter-warp pq handles pixel g*4+pq; lane ql its channels 4*ql..+3 of a chunk
         constexpr int NCHK = C / CHK;
         const int nchunks = ntiles * NCHK;
-        float rb[4] = {0.f, 0.f, 0.f, 0.f};                                // |diff| sums: quarter-warp pq keeps channel chunk pq (4 channels per lane)
+        float rb[NCHK * 4];                                                // |diff| sums of this lane's 4 channels of every chunk (its quarter's pixels)
+#pragma unroll
+        for (int u = 0; u < NCHK * 4; ++u) rb[u] = 0.f;
         int cur_b = -1, ndump = 0;
         const uint32_t win0 = smem_u32(base + SM::off_win);
 
         auto dump_rb = [&]() {
             if (ndump > 0) mbar_wait_parked(rbfree, (ndump - 1) & 1);       // the algebra warps consumed the previous hand-over
-            if (pq < NCHK) *reinterpret_cast<float4*>(sRbs + g * 128 + CHK * pq + 4 * ql) = make_float4(rb[0], rb[1], rb[2], rb[3]);
+#pragma unroll
+            for (int u = 0; u < NCHK * 4; ++u) { rb[u] += __shfl_xor_sync(0xffffffffu, rb[u], 8); rb[u] += __shfl_xor_sync(0xffffffffu, rb[u], 16); }
+            if (pq == 0) {
+#pragma unroll
+                for (int c = 0; c < NCHK; ++c)
+                    *reinterpret_cast<float4*>(sRbs + g * 128 + CHK * c + 4 * ql) = make_float4(rb[4 * c], rb[4 * c + 1], rb[4 * c + 2], rb[4 * c + 3]);
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(rbdump);
-            rb[0] = rb[1] = rb[2] = rb[3] = 0.f;
+#pragma unroll
+            for (int u = 0; u < NCHK * 4; ++u) rb[u] = 0.f;
             ++ndump;
         };
-        // conv1 (streaming, read once): the NCHK chunk loads of this lane's pixel are issued one whole tile ahead (slot c is refilled for
-        // tile j+1 as soon as chunk c of tile j has been consumed), so 16 warps x 32 lanes x 64 B stay in flight in registers
-        float4 c1v[NCHK];
-        const float* c1next = nullptr;
-        auto c1_pointer = [&](int jt) -> const float* {
-            if (jt >= ntiles) return nullptr;
-            const TileCoord tn = tile_coord(prm, t_begin + jt);
-            const int pxi = g * 4 + pq, gx = tn.tx0 + (pxi & 7), gy = tn.ty0 + (pxi >> 3);
-            if (gx >= prm.grid_w || gy >= prm.grid_h) return nullptr;
-            return prm.conv1 + ((size_t)tn.b * N + (size_t)gy * prm.grid_w + gx) * C + 4 * ql;
-        };
-        {
-            const float* c1p = c1_pointer(0);
-#pragma unroll
-            for (int c = 0; c < NCHK; ++c) c1v[c] = c1p ? ld_stream_f4(c1p + c * CHK) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
         // tile jt fits the staged window?  (every gather warp evaluates the same 16 ints: no hand-over needed)
         auto decide = [&](int jt, int& wx0, int& wy0) -> bool {
             const int4* bx = reinterpret_cast<const int4*>(sBox + (jt % NREC) * W0 * 4);
@@ -344,22 +382,23 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             wx0 = xmn; wy0 = ymn;
             return prm.force_direct == 0 && xmn <= xmx && (xmx - xmn) < WX && (ymx - ymn) < WY;
         };
-        // producer duty of gather warp 0 (its lane 0): chunk q = (tile, 32-channel chunk) -> window buffer q % NWB
+        // producer duty of gather warp 0 (its lane 0): chunk q = (tile, 32-channel chunk) -> ring buffer q % NWB: the conv1 chunk of the tile
+        // (always) and, when the tile's taps fit, the F2 window chunk.  Tile coordinates come from the geometry warps (sTile).
         auto issue_chunk = [&](int q) {
             const int jt = q / NCHK, c = q - jt * NCHK, buf = q % NWB;
             mbar_wait_parked(&recs[jt % NREC], (jt / NREC) & 1);
+            const int* ti = sTile + (jt % NREC) * 4;
+            const int b = ti[0], tx0 = ti[1], ty0 = ti[2];
             int wx0, wy0;
-#ifdef BANET_TC7_DBG_NOTMA          // timing experiment only: staged tiles complete without loading anything (results are garbage)
-            if (false) {
+#ifdef BANET_TC7_DBG_NOTMA          // timing experiment only: nothing is loaded (results are garbage)
+            mbar_arrive(&winfull[buf]); (void)b; (void)tx0; (void)ty0; (void)wx0; (void)wy0; (void)c;
 #else
-            if (decide(jt, wx0, wy0)) {
+            const bool staged = decide(jt, wx0, wy0);
+            unsigned char* dst = base + SM::off_win + buf * WBUF;
+            mbar_arrive_expect_tx(&winfull[buf], (staged ? WIN_TX_BYTES : 0) + C1_BYTES);
+            tma_load_4d(dst + WIN_BYTES, &tmapC, c * CHK, tx0, ty0, b, &winfull[buf]);
+            if (staged) tma_load_4d(dst, &tmapF, c * CHK, wx0, wy0, b, &winfull[buf]);
 #endif
-                const int b = sTile[(jt % NREC) * 4];
-                mbar_arrive_expect_tx(&winfull[buf], WIN_TX_BYTES);
-                tma_load_4d(base + SM::off_win + buf * WIN_BYTES, &tmapF, c * CHK, wx0, wy0, b, &winfull[buf]);
-            } else {
-                mbar_arrive(&winfull[buf]);                   // direct-tap tile: nothing to stage, the phase completes at once
-            }
         };
         if (g == 0) { if (lane == 0) { for (int q = 0; q < NWB && q < nchunks; ++q) issue_chunk(q); } __syncwarp(); }
 
@@ -370,7 +409,8 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             if (b != cur_b) { if (cur_b >= 0) dump_rb(); cur_b = b; }
             int wx0, wy0;
             const bool staged = decide(j, wx0, wy0);
-            float* rec = sRec + (s * TILE + g * 4 + pq) * REC;
+            const int pxi = g * 4 + pq;
+            float* rec = sRec + (s * TILE + pxi) * REC;
             const float mask = rec[4];
             const uint2 ryp = *reinterpret_cast<const uint2*>(rec);
             const float4 r12 = *reinterpret_cast<const float4*>(rec + 12);
@@ -378,8 +418,8 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             const uint32_t cxa = __float_as_uint(r12.z), cxb = __float_as_uint(r12.w);
             const int ym = ryp.x & 0xffffu, y0 = ryp.x >> 16, y1 = ryp.y & 0xffffu, yp = ryp.y >> 16;
             const int xm = cxa & 0xffffu, x0 = cxa >> 16, x1 = cxb & 0xffffu, xp = cxb >> 16;
-            c1next = c1_pointer(j + 1);
             const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+            const u64 W00 = pk2(w00, w00), W01 = pk2(w01, w01), W10 = pk2(w10, w10), W11 = pk2(w11, w11);
             // tap addresses: staged = byte offsets inside a window buffer; direct = float offsets inside the pair's F2 map
             uint32_t rM, r0, r1, rP, oM, o0, o1, oP;
             if (staged) {
@@ -392,67 +432,67 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                 oM = (uint32_t)(xm * c2 + 4 * ql); o0 = (uint32_t)(x0 * c2 + 4 * ql); o1 = (uint32_t)(x1 * c2 + 4 * ql); oP = (uint32_t)(xp * c2 + 4 * ql);
             }
             const float* imgb = prm.conv2 + (size_t)b * h * w * c2;
-            float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
+            const uint32_t c1off = (uint32_t)(WIN_BYTES + pxi * 128 + ql * 16);
+            u64 m11 = 0ull, m12 = 0ull, m22 = 0ull, q1 = 0ull, q2 = 0ull;        // packed (2 channels) sums of (2gx)^2, (2gx)(2gy), (2gy)^2, (2gx) d, (2gy) d
 #pragma unroll
             for (int c = 0; c < NCHK; ++c) {
                 const int q = j * NCHK + c, buf = q % NWB;
                 mbar_wait_parked(&winfull[buf], (q / NWB) & 1);
-                float4 ad = make_float4(0.f, 0.f, 0.f, 0.f);
 #ifdef BANET_TC7_DBG_NOGATHER       // timing experiment only: no tap loads / arithmetic (results are garbage)
                 if (false) {
 #else
                 if (mask != 0.f) {
 #endif
-                    // grad_fixed on the fly (bundlenet.py:92-100): gx, gy = 0.5 * central differences at the 4 bilinear taps.  Two phases so that
-                    // at most 8 of the 12 taps are live at once (88-register budget): A = the two middle rows (f2, gx and the part of gy they
-                    // carry), B = the rows above / below.  The empty asm ties phase B's first address to a phase-A result: ptxas may not hoist
-                    // the second group of loads above the first group's arithmetic.
-                    float4 aM0, a00, a10, aP0, aM1, a01, a11, aP1;
-                    uint32_t wb = 0; const float* img = nullptr;
+                    // grad_fixed on the fly (bundlenet.py:92-100): 2gx, 2gy = central differences at the 4 bilinear taps, as sums of positive minus sums of
+                    // negative terms in packed fp32 pairs; the factors 1/2 are applied once per pixel.  Two load phases (the two middle rows, then the rows
+                    // above / below) keep at most 8 of the 12 taps live; the empty asm ties phase B's address to a phase-A result so that ptxas cannot hoist it.
+                    const uint32_t wb = win0 + buf * WBUF;
+                    ulonglong2 aM0, a00, a10, aP0, aM1, a01, a11, aP1;
+                    const float* img = imgb + c * CHK;
                     if (staged) {
-                        wb = win0 + buf * WIN_BYTES;
-                        aM0 = lds4(wb + r0 + oM); a00 = lds4(wb + r0 + o0); a10 = lds4(wb + r0 + o1); aP0 = lds4(wb + r0 + oP);
-                        aM1 = lds4(wb + r1 + oM); a01 = lds4(wb + r1 + o0); a11 = lds4(wb + r1 + o1); aP1 = lds4(wb + r1 + oP);
+                        aM0 = lds2x64(wb + r0 + oM); a00 = lds2x64(wb + r0 + o0); a10 = lds2x64(wb + r0 + o1); aP0 = lds2x64(wb + r0 + oP);
+                        aM1 = lds2x64(wb + r1 + oM); a01 = lds2x64(wb + r1 + o0); a11 = lds2x64(wb + r1 + o1); aP1 = lds2x64(wb + r1 + oP);
                     } else {
-                        img = imgb + c * CHK;
-                        aM0 = ldg4(img + r0 + oM); a00 = ldg4(img + r0 + o0); a10 = ldg4(img + r0 + o1); aP0 = ldg4(img + r0 + oP);
-                        aM1 = ldg4(img + r1 + oM); a01 = ldg4(img + r1 + o0); a11 = ldg4(img + r1 + o1); aP1 = ldg4(img + r1 + oP);
+                        aM0 = ldg2x64(img + r0 + oM); a00 = ldg2x64(img + r0 + o0); a10 = ldg2x64(img + r0 + o1); aP0 = ldg2x64(img + r0 + oP);
+                        aM1 = ldg2x64(img + r1 + oM); a01 = ldg2x64(img + r1 + o0); a11 = ldg2x64(img + r1 + o1); aP1 = ldg2x64(img + r1 + oP);
                     }
-                    const float4 f1 = c1v[c];
-                    float4 dv, gxv, gyv;
-#define BANET_A(F)                                                                                                   \
-                    dv.F = f1.F - (w00 * a00.F + w01 * a10.F + w10 * a01.F + w11 * a11.F);                           \
-                    gxv.F = 0.5f * (w00 * (a10.F - aM0.F) + w01 * (aP0.F - a00.F) + w10 * (a11.F - aM1.F) + w11 * (aP1.F - a01.F)); \
-                    gyv.F = (w00 * a01.F - w10 * a00.F) + (w01 * a11.F - w11 * a10.F);
-                    BANET_A(x) BANET_A(y) BANET_A(z) BANET_A(w)
+                    const ulonglong2 f1 = lds2x64(wb + c1off);
+                    u64 d[2], gx[2], gyP[2], gyN[2];
+#define BANET_A(H, F)                                                                                               \
+                    {                                                                                               \
+                        u64 S = mul2(a00.F, W00); S = fma2(a10.F, W01, S); S = fma2(a01.F, W10, S); S = fma2(a11.F, W11, S);           \
+                        d[H] = sub2(f1.F, S);                                                                       \
+                        u64 P = mul2(a10.F, W00); P = fma2(aP0.F, W01, P); P = fma2(a11.F, W10, P); P = fma2(aP1.F, W11, P);           \
+                        u64 Nn = mul2(aM0.F, W00); Nn = fma2(a00.F, W01, Nn); Nn = fma2(aM1.F, W10, Nn); Nn = fma2(a01.F, W11, Nn);    \
+                        gx[H] = sub2(P, Nn);                                                                        \
+                        gyP[H] = fma2(a11.F, W01, mul2(a01.F, W00));                                                \
+                        gyN[H] = fma2(a10.F, W11, mul2(a00.F, W10));                                                \
+                    }
+                    BANET_A(0, x) BANET_A(1, y)
 #undef BANET_A
-                    uint32_t dep = __float_as_uint(gyv.w) & 0u;
-                    asm volatile("" : "+r"(dep) : "f"(dv.x), "f"(gxv.y));
-                    float4 a0m, a1m, a0p, a1p;
+                    uint32_t dep = (uint32_t)(d[0] & 0ull);
+                    asm volatile("" : "+r"(dep) : "l"(gx[1]), "l"(gyP[0]));
+                    ulonglong2 a0m, a1m, a0p, a1p;
                     if (staged) {
-                        wb += dep;
-                        a0m = lds4(wb + rM + o0); a1m = lds4(wb + rM + o1); a0p = lds4(wb + rP + o0); a1p = lds4(wb + rP + o1);
+                        const uint32_t wb2 = wb + dep;
+                        a0m = lds2x64(wb2 + rM + o0); a1m = lds2x64(wb2 + rM + o1); a0p = lds2x64(wb2 + rP + o0); a1p = lds2x64(wb2 + rP + o1);
                     } else {
-                        img += dep;
-                        a0m = ldg4(img + rM + o0); a1m = ldg4(img + rM + o1); a0p = ldg4(img + rP + o0); a1p = ldg4(img + rP + o1);
+                        const float* img2 = img + dep;
+                        a0m = ldg2x64(img2 + rM + o0); a1m = ldg2x64(img2 + rM + o1); a0p = ldg2x64(img2 + rP + o0); a1p = ldg2x64(img2 + rP + o1);
                     }
-#define BANET_B(F)                                                                                                   \
-                    {                                                                                                \
-                        const float gy = 0.5f * (gyv.F - w00 * a0m.F + w10 * a0p.F - w01 * a1m.F + w11 * a1p.F);     \
-                        m11 = fmaf(gxv.F, gxv.F, m11); m12 = fmaf(gxv.F, gy, m12); m22 = fmaf(gy, gy, m22);          \
-                        q1 = fmaf(gxv.F, dv.F, q1); q2 = fmaf(gy, dv.F, q2);                                         \
-                        ad.F = fabsf(dv.F);                                                                          \
+#define BANET_B(H, F, K0)                                                                                           \
+                    {                                                                                               \
+                        const u64 P = fma2(a1p.F, W11, fma2(a0p.F, W10, gyP[H]));                                   \
+                        const u64 Nn = fma2(a1m.F, W01, fma2(a0m.F, W00, gyN[H]));                                  \
+                        const u64 gy = sub2(P, Nn);                                                                 \
+                        m11 = fma2(gx[H], gx[H], m11); m12 = fma2(gx[H], gy, m12); m22 = fma2(gy, gy, m22);          \
+                        q1 = fma2(gx[H], d[H], q1); q2 = fma2(gy, d[H], q2);                                         \
+                        const float2 dd = upk2(d[H]);                                                               \
+                        rb[4 * c + K0] += fabsf(dd.x); rb[4 * c + K0 + 1] += fabsf(dd.y);                             \
                     }
-                    BANET_B(x) BANET_B(y) BANET_B(z) BANET_B(w)
+                    BANET_B(0, x, 0) BANET_B(1, y, 2)
 #undef BANET_B
                 }
-                c1v[c] = c1next ? ld_stream_f4(c1next + c * CHK) : make_float4(0.f, 0.f, 0.f, 0.f);      // slot c: next tile's chunk
-                // |diff| of the 4 pixels of the warp -> the quarter that owns chunk c
-                ad.x += __shfl_xor_sync(0xffffffffu, ad.x, 8); ad.y += __shfl_xor_sync(0xffffffffu, ad.y, 8);
-                ad.z += __shfl_xor_sync(0xffffffffu, ad.z, 8); ad.w += __shfl_xor_sync(0xffffffffu, ad.w, 8);
-                ad.x += __shfl_xor_sync(0xffffffffu, ad.x, 16); ad.y += __shfl_xor_sync(0xffffffffu, ad.y, 16);
-                ad.z += __shfl_xor_sync(0xffffffffu, ad.z, 16); ad.w += __shfl_xor_sync(0xffffffffu, ad.w, 16);
-                if (pq == c) { rb[0] += ad.x; rb[1] += ad.y; rb[2] += ad.z; rb[3] += ad.w; }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&winfree[buf]);
                 if (g == 0) {                                // refill the buffer just released with the chunk NWB ahead
@@ -460,10 +500,14 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                     __syncwarp();
                 }
             }
-            m11 = qsum8(m11); m12 = qsum8(m12); m22 = qsum8(m22); q1 = qsum8(q1); q2 = qsum8(q2);
+            float s11, s12, s22, sq1, sq2;
+            { const float2 t = upk2(m11); s11 = 0.25f * (t.x + t.y); } { const float2 t = upk2(m12); s12 = 0.25f * (t.x + t.y); }
+            { const float2 t = upk2(m22); s22 = 0.25f * (t.x + t.y); } { const float2 t = upk2(q1); sq1 = 0.5f * (t.x + t.y); }
+            { const float2 t = upk2(q2); sq2 = 0.5f * (t.x + t.y); }
+            s11 = qsum8(s11); s12 = qsum8(s12); s22 = qsum8(s22); sq1 = qsum8(sq1); sq2 = qsum8(sq2);
             if (ql == 0) {               // totals overwrite dx,dy / tap columns / n of this pixel's record (no longer needed)
-                *reinterpret_cast<float4*>(rec + 12) = make_float4(m11, m12, m22, q1);
-                rec[11] = q2;
+                *reinterpret_cast<float4*>(rec + 12) = make_float4(s11, s12, s22, sq1);
+                rec[11] = sq2;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&gath[s]);
@@ -709,13 +753,13 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
 
 
 template <int NCH, int MODE, int KBLK = 4>
-static int launch7(const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildParams& prm, int grid, cudaStream_t st)
+static int launch7(const CUtensorMap& tmB, const CUtensorMap& tmF, const CUtensorMap& tmC, const BuildParams& prm, int grid, cudaStream_t st)
 {
     auto kern = lm_build_tc7_kernel<NCH, MODE, KBLK>;
     const int smem = Smem<MODE, NCH>::bytes;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) { set_error("lm_build_tc7: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-    kern<<<grid, THREADS, smem, st>>>(tmB, tmF, prm);
+    kern<<<grid, THREADS, smem, st>>>(tmB, tmF, tmC, prm);
     BANET_CUDA_LAUNCH_CHECK("lm_build_tc7_kernel launch");
     return BANET_OK;
 }
@@ -725,11 +769,12 @@ static int launch7(const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildPa
 bool lm_build_tc7_supported(int mode, int nch, int kblk) { return (mode == 1 || mode == 2) && (nch == 1 || nch == 2) && kblk == 4; }
 void lm_build_tc7_window(int* wx, int* wy) { *wx = v7::WX; *wy = v7::BOX_Y; }
 
-int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildParams& prm, int grid, cudaStream_t st)
+int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, const CUtensorMap& tmF, const CUtensorMap& tmC, const BuildParams& prm, int grid,
+                        cudaStream_t st)
 {
     BANET_REQUIRE(lm_build_tc7_supported(mode, nch, kblk), BANET_ERR_UNSUPPORTED, "lm_build_tc7: mode %d / C=%d / K=%d not instantiated", mode, 64 * nch, 32 * kblk);
-    if (nch == 2) return mode == 1 ? v7::launch7<2, 1>(tmB, tmF, prm, grid, st) : v7::launch7<2, 2>(tmB, tmF, prm, grid, st);
-    return mode == 1 ? v7::launch7<1, 1>(tmB, tmF, prm, grid, st) : v7::launch7<1, 2>(tmB, tmF, prm, grid, st);
+    if (nch == 2) return mode == 1 ? v7::launch7<2, 1>(tmB, tmF, tmC, prm, grid, st) : v7::launch7<2, 2>(tmB, tmF, tmC, prm, grid, st);
+    return mode == 1 ? v7::launch7<1, 1>(tmB, tmF, tmC, prm, grid, st) : v7::launch7<1, 2>(tmB, tmF, tmC, prm, grid, st);
 }
 
 }  // namespace banet

@@ -32,7 +32,8 @@ namespace banet {
 constexpr int TC_TILE = 64;
 
 int lm_build_tc6_launch(int mode, bool fly, int nch, int kblk, const CUtensorMap& tm, const BuildParams& prm, int grid, cudaStream_t st);
-int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, const CUtensorMap& tmF, const BuildParams& prm, int grid, cudaStream_t st);
+int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, const CUtensorMap& tmF, const CUtensorMap& tmC, const BuildParams& prm, int grid,
+                        cudaStream_t st);
 bool lm_build_tc7_supported(int mode, int nch, int kblk);
 
 static banet_tuning_t g_tuning = {0, 0, 4};
@@ -107,7 +108,10 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
         int wx = 0, wy = 0; lm_build_tc7_window(&wx, &wy);
         rc = make_tmap_f32_nhwc(&tmF, lv->conv2, lv->nb, lv->h, lv->w, lv->conv2_channels, 32, wx, wy);
         if (rc) return rc;
-        rc = lm_build_tc7_launch(mode, nch, kblk, tm, tmF, prm, plan.grid, st);
+        CUtensorMap tmC;        // conv1 chunk of an 8x8 tile: 32 channels x 8 x 8 pixels of [nb, grid_h, grid_w, C]
+        rc = make_tmap_f32_nhwc(&tmC, lv->conv1, lv->nb, lv->grid_h, lv->grid_w, lv->C, 32, 8, 8);
+        if (rc) return rc;
+        rc = lm_build_tc7_launch(mode, nch, kblk, tm, tmF, tmC, prm, plan.grid, st);
     } else {
         rc = lm_build_tc6_launch(mode, fly, nch, kblk, tm, prm, plan.grid, st);
     }
