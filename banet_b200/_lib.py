@@ -60,6 +60,7 @@ SIGNATURES = {
     "banet_compute_coordinates": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p, c_stream]),
     "banet_grad_fixed_concat": (C.c_int, [c_float_p] + [C.c_int] * 5 + [c_float_p, c_stream]),
     "banet_resample": (C.c_int, [c_float_p, c_float_p, C.c_float] + [C.c_int] * 5 + [c_float_p, c_stream]),
+    "banet_interpolate2d": (C.c_int, [c_float_p, c_float_p, C.c_float] + [C.c_int] * 5 + [c_float_p, c_float_p, c_stream]),
     "banet_lm_build_workspace_bytes": (C.c_size_t, [C.POINTER(BanetLevel), C.c_int]),
     "banet_lm_build": (C.c_int, [C.POINTER(BanetLevel)] + [c_float_p] * 3 + [C.c_int] + [c_float_p] * 4
                        + [C.c_void_p, C.c_size_t, c_stream]),

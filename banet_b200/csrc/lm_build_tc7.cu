@@ -16,6 +16,12 @@
 //   tile order:   bands of `band_rows` tile rows walked column by column, so that the window halos of vertically AND horizontally
 //                 adjacent tiles are re-read from L2 while they are still resident (generation 6 walks rows: vertical halo from HBM).
 //
+//   division of labour (measured, profiles/r02b_*: with the taps on LDS the kernel turned instruction-issue / role-latency bound, so work moved to
+//                 where the warps are): the 16 gather warps also derive s_n = jd^T M jd and write the MMA operands of their pixel — the R row
+//                 rna(s_n b_n) and the precision mode's side of the basis tile (stochastic tf32 rounding in place, or A_lo) — which the 4
+//                 algebra warps did in generation 6; the geometry warps only form b.W and the warp; the per-channel arithmetic runs on packed
+//                 fp32 pairs (FFMA2 / FMUL2 / FADD2); conv1 arrives with the window (one 4-D TMA box {32 ch, 8, 8, pair} per chunk).
+//
 // Roles (896 threads, 1 CTA / SM) and barriers as generation 6, plus winfull[NWB] (TMA landed, count 1 + tx) / winfree[NWB] (count GW).
 #include "common.cuh"
 #include "lm_build.h"
@@ -71,8 +77,8 @@ template <int MODE, int NCH> struct Smem {
     static constexpr int off_misc = off_win + NWB * WBUF;
     static constexpr int off_bar = off_misc;                           // 22 + 2*NWB mbarriers (<= 30)
     static constexpr int off_tmem = off_bar + 30 * 8;
-    static constexpr int off_tile = off_misc + 256;                    // [NREC][4] ints: pair index of the tile in record buffer s
-    static constexpr int off_box = off_tile + 64;                      // [NREC][W0][4] ints: tap bounding box (xmin,xmax,ymin,ymax) per geometry warp
+    static constexpr int off_tile = off_misc + 256;                    // [NREC][8] ints: pair, tx0, ty0, fx, fy (float bits), dither seed of the tile in record buffer s
+    static constexpr int off_box = off_tile + 128;                     // [NREC][W0][4] ints: tap bounding box (xmin,xmax,ymin,ymax) per geometry warp
     static constexpr int off_pose = off_box + NREC * W0 * 16;          // [W0][16] floats (private to each geometry warp)
     static constexpr int off_w = off_pose + W0 * 16 * 4;               // [W0][128] floats: W of the pair (private to each geometry warp)
     static constexpr int off_rec = off_w + W0 * 128 * 4;               // [NREC][TILE][REC] floats
@@ -287,20 +293,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                     const float4 bv = *reinterpret_cast<const float4*>(As + blk * 8192 + sw128_32b_off(nlr, c));
                     const float4 w4 = *reinterpret_cast<const float4*>(myW + blk * 32 + c * 4);
                     acc.x = fmaf(bv.x, w4.x, acc.x); acc.y = fmaf(bv.y, w4.y, acc.y); acc.z = fmaf(bv.z, w4.z, acc.z); acc.w = fmaf(bv.w, w4.w, acc.w);
-                    if constexpr (MODE == 1) {
-                        // single-pass mode: round the basis tile to tf32 IN PLACE with a dither hashed from (iterate, pixel, column):
-                        // unbiased, changes with the iterate, and a pure function of the inputs (see generation 6 for the measurements)
-                        uint32_t hsh = dseed ^ ((uint32_t)n * 0x9E3779B1u) ^ ((uint32_t)(blk * 8 + c) * 0x85EBCA77u);
-                        hsh ^= hsh >> 16; hsh *= 0x7FEB352Du; hsh ^= hsh >> 15;
-                        uint32_t hs2 = hsh * 0x846CA68Bu; hs2 ^= hs2 >> 16;
-                        *reinterpret_cast<float4*>(const_cast<unsigned char*>(As) + blk * 8192 + sw128_32b_off(nlr, c)) =
-                            make_float4(__uint_as_float((__float_as_uint(bv.x) + (hsh & 0x1fffu)) & 0xFFFFE000u),
-                                        __uint_as_float((__float_as_uint(bv.y) + ((hsh >> 13) & 0x1fffu)) & 0xFFFFE000u),
-                                        __uint_as_float((__float_as_uint(bv.z) + (hs2 & 0x1fffu)) & 0xFFFFE000u),
-                                        __uint_as_float((__float_as_uint(bv.w) + ((hs2 >> 13) & 0x1fffu)) & 0xFFFFE000u));
-                    }
                 }
-                if constexpr (MODE == 1) fence_proxy_async_smem();      // the MMA reads this stage through the async proxy
                 mydot = (acc.x + acc.y) + (acc.z + acc.w);
                 mydot += __shfl_xor_sync(0xffffffffu, mydot, 16);
             }
@@ -341,7 +334,8 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             bymin = __reduce_min_sync(0xffffffffu, bymin); bymax = __reduce_max_sync(0xffffffffu, bymax);
             if (lane == 0) {
                 *reinterpret_cast<int4*>(sBox + (sr * W0 + gwi) * 4) = make_int4(bxmin, bxmax, bymin, bymax);
-                if (gwi == 0) { sTile[sr * 4] = b; sTile[sr * 4 + 1] = tc.tx0; sTile[sr * 4 + 2] = tc.ty0; }
+                if (gwi == 0) { sTile[sr * 8] = b; sTile[sr * 8 + 1] = tc.tx0; sTile[sr * 8 + 2] = tc.ty0;
+                    sTile[sr * 8 + 3] = __float_as_int(myPose[12]); sTile[sr * 8 + 4] = __float_as_int(myPose[13]); sTile[sr * 8 + 5] = (int)dseed; }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&recs[sr]);
@@ -387,7 +381,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         auto issue_chunk = [&](int q) {
             const int jt = q / NCHK, c = q - jt * NCHK, buf = q % NWB;
             mbar_wait_parked(&recs[jt % NREC], (jt / NREC) & 1);
-            const int* ti = sTile + (jt % NREC) * 4;
+            const int* ti = sTile + (jt % NREC) * 8;
             const int b = ti[0], tx0 = ti[1], ty0 = ti[2];
             int wx0, wy0;
 #ifdef BANET_TC7_DBG_NOTMA          // timing experiment only: nothing is loaded (results are garbage)
@@ -405,7 +399,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         for (int j = 0; j < ntiles; ++j) {
             const int s = j % NREC;
             mbar_wait_parked(&recs[s], (j / NREC) & 1);
-            const int b = sTile[s * 4];
+            const int b = sTile[s * 8];
             if (b != cur_b) { if (cur_b >= 0) dump_rb(); cur_b = b; }
             int wx0, wy0;
             const bool staged = decide(j, wx0, wy0);
@@ -414,6 +408,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             const float mask = rec[4];
             const uint2 ryp = *reinterpret_cast<const uint2*>(rec);
             const float4 r12 = *reinterpret_cast<const float4*>(rec + 12);
+            const float4 rgeo = *reinterpret_cast<const float4*>(rec + 8);        // rx, ry, rz, n
             const float dx = r12.x, dy = r12.y;
             const uint32_t cxa = __float_as_uint(r12.z), cxb = __float_as_uint(r12.w);
             const int ym = ryp.x & 0xffffu, y0 = ryp.x >> 16, y1 = ryp.y & 0xffffu, yp = ryp.y >> 16;
@@ -505,16 +500,60 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             { const float2 t = upk2(m22); s22 = 0.25f * (t.x + t.y); } { const float2 t = upk2(q1); sq1 = 0.5f * (t.x + t.y); }
             { const float2 t = upk2(q2); sq2 = 0.5f * (t.x + t.y); }
             s11 = qsum8(s11); s12 = qsum8(s12); s22 = qsum8(s22); sq1 = qsum8(sq1); sq2 = qsum8(sq2);
+            // s_n = jd^T M jd of this quarter's pixel (DepthJacobianMatrix, bundlenet.py:63-74), every lane of the quarter
+            float sn;
+            {
+                const float x = rec[5], y = rec[6], iZ = rec[7];
+                const float fx = __int_as_float(sTile[s * 8 + 3]), fy = __int_as_float(sTile[s * 8 + 4]);
+                const float jd0 = fx * ((rgeo.x - rgeo.z * x) * iZ), jd1 = fy * ((rgeo.y - rgeo.z * y) * iZ);
+                const float u0 = s11 * jd0 + s12 * jd1, u1 = s12 * jd0 + s22 * jd1;
+                sn = (mask != 0.f) ? jd0 * u0 + jd1 * u1 : 0.f;
+            }
+            __syncwarp();                                    // every lane has read its record before the totals overwrite part of it
             if (ql == 0) {               // totals overwrite dx,dy / tap columns / n of this pixel's record (no longer needed)
                 *reinterpret_cast<float4*>(rec + 12) = make_float4(s11, s12, s22, sq1);
                 rec[11] = sq2;
             }
+            // ---- scaling pass: R row = rna(s_n * b_n) (the MMA's B operand), and the A-operand side of the precision mode, for this quarter's pixel:
+            //      16 floats per lane = its 16-B chunk in each of the 4 basis blocks (a quarter reads / writes one whole 128-B row: conflict-free).
+            //      Moved here from the 4 algebra warps: 16 warps share the work and the algebra -> MMA path of a tile becomes short.
+            if (j > 0) mbar_wait_parked(rfree, (j - 1) & 1);                  // MMAs of tile j-1 done: R (and A_lo) are free
+            {
+                const int st = j % NST;
+                mbar_wait_parked(&fullB[st], (j / NST) & 1);                  // long complete (the geometry warps needed it)
+                unsigned char* As = base + SM::off_A + st * STAGE_A;
+                unsigned char* Rs = base + SM::off_R;
+                const uint32_t rowo = sw128_32b_off(pxi, ql);
+                uint32_t hbase = 0;
+                if constexpr (MODE == 1) hbase = (uint32_t)sTile[s * 8 + 5] ^ ((uint32_t)__float_as_int(rgeo.w) * 0x9E3779B1u);
+#pragma unroll
+                for (int blk = 0; blk < KBLK; ++blk) {
+                    const uint32_t off = blk * 8192 + rowo;
+                    const float4 bv = *reinterpret_cast<const float4*>(As + off);
+                    *reinterpret_cast<float4*>(Rs + off) = make_float4(tf32_rna_bits(sn * bv.x), tf32_rna_bits(sn * bv.y), tf32_rna_bits(sn * bv.z), tf32_rna_bits(sn * bv.w));
+                    if constexpr (MODE == 1) {
+                        // single-pass mode: the basis tile is rounded to tf32 IN PLACE with a dither hashed from (iterate, pixel, column): unbiased, changes
+                        // with the iterate, and a pure function of the inputs (see generation 6 for the measurements that led here)
+                        uint32_t hsh = hbase ^ ((uint32_t)(blk * 8 + ql) * 0x85EBCA77u);
+                        hsh ^= hsh >> 16; hsh *= 0x7FEB352Du; hsh ^= hsh >> 15;
+                        uint32_t hs2 = hsh * 0x846CA68Bu; hs2 ^= hs2 >> 16;
+                        *reinterpret_cast<float4*>(As + off) =
+                            make_float4(__uint_as_float((__float_as_uint(bv.x) + (hsh & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.y) + ((hsh >> 13) & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.z) + (hs2 & 0x1fffu)) & 0xFFFFE000u),
+                                        __uint_as_float((__float_as_uint(bv.w) + ((hs2 >> 13) & 0x1fffu)) & 0xFFFFE000u));
+                    }
+                    if constexpr (MODE >= 2)
+                        *reinterpret_cast<float4*>(base + SM::off_Alo + off) = make_float4(bv.x - tf32_trunc(bv.x), bv.y - tf32_trunc(bv.y), bv.z - tf32_trunc(bv.z), bv.w - tf32_trunc(bv.w));
+                }
+            }
+            fence_proxy_async_smem();                        // the MMA reads R / A / A_lo through the async proxy
             __syncwarp();
             if (lane == 0) mbar_arrive(&gath[s]);
         }
         if (cur_b >= 0) dump_rb();
     } else if (warp < W0 + GW + AW) {
-        // ===================================================================== algebra warps: 2x7 algebra, R rows, MMA + TMA issue
+        // ===================================================================== algebra warps: 2x7 algebra (H_cc, g_c, [v | t]), MMA + TMA issue
         setmaxnreg_dec<64>();
         const int awi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*awi .. 16*awi+15
         const int atid = tid - (W0 + GW) * 32;
@@ -578,7 +617,6 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             const int s = j % NST, sr = j % NREC;
             const bool last_of_pair = (++rr == prm.tiles_per_pair) || (j == ntiles - 1);
             if (rr == prm.tiles_per_pair) rr = 0;
-            const unsigned char* As = base + SM::off_A + s * STAGE_A;
             if (j > 0) {
                 // MMAs of tile j-1 done: R / A_lo and stage (j-1) % NST are free.  Refill the stage BEFORE waiting for the gather of tile j: the
                 // window producer (gather warp 0) looks ahead into tile j+1 and waits for its records, i.e. for the geometry warps, i.e. for
@@ -587,7 +625,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                 if (awi == 0 && lane == 0 && j - 1 + NST < ntiles) issue_tma(j - 1 + NST);
             }
             mbar_wait_parked(&gath[sr], (j / NREC) & 1);
-            const int b = sTile[sr * 4];
+            const int b = sTile[sr * 8];
             if (b != scale_b) { scale_b = b; ++sspan; fx = __ldg(prm.intr + b * 4); fy = __ldg(prm.intr + b * 4 + 1); }
             float ext[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (lane < 16) {                                 // thread per pixel (bundlenet.py:49-74)
@@ -620,7 +658,6 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&recfree[sr]);        // the record buffer may be refilled (everything needed is in registers)
-            const float sn = __shfl_sync(0xffffffffu, ext[7], r16);   // s_n of this lane's row
             mbar_wait_parked(&fullB[s], (j / NST) & 1);      // long complete; orders the TMA writes before the reads below
             if (lane < 16) {                                 // R columns 128..134 = [v(6) | t], column 135 stays zero
                 const float4 e0 = make_float4(tf32_rna(ext[0]), tf32_rna(ext[1]), tf32_rna(ext[2]), tf32_rna(ext[3]));
@@ -632,24 +669,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                     *reinterpret_cast<float4*>(base + SM::off_Rlo + EXTB * 8192 + sw128_32b_off(nlr, 1)) = make_float4(ext[4] - e1.x, ext[5] - e1.y, ext[6] - e1.z, 0.f);
                 }
             }
-            // R rows (and the split parts): elementwise on the lane's half row, so walk the PHYSICAL 16-B slots (rotated by the row: every
-            // quarter-warp touches 8 distinct bank groups) and skip the swizzle arithmetic
-            const uint32_t rowoff = hf * 16384 + nlr * 128;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if (KBLK != 4 && 2 * hf + (i >> 3) >= KBLK) continue;
-                const uint32_t off = rowoff + (i >> 3) * 8192 + (((i & 7) + r16) & 7) * 16;
-                const float4 bv = *reinterpret_cast<const float4*>(As + off);
-                const float4 pv = make_float4(sn * bv.x, sn * bv.y, sn * bv.z, sn * bv.w);
-                float4 hv;
-                if constexpr (MODE == 3) hv = make_float4(tf32_rna(pv.x), tf32_rna(pv.y), tf32_rna(pv.z), tf32_rna(pv.w));
-                else hv = make_float4(tf32_rna_bits(pv.x), tf32_rna_bits(pv.y), tf32_rna_bits(pv.z), tf32_rna_bits(pv.w));   // MMA drops the low 13 bits
-                *reinterpret_cast<float4*>(Rs + off) = hv;
-                if constexpr (MODE >= 2)
-                    *reinterpret_cast<float4*>(base + SM::off_Alo + off) = make_float4(bv.x - tf32_trunc(bv.x), bv.y - tf32_trunc(bv.y), bv.z - tf32_trunc(bv.z), bv.w - tf32_trunc(bv.w));
-                if constexpr (MODE == 3)
-                    *reinterpret_cast<float4*>(base + SM::off_Rlo + off) = make_float4(pv.x - hv.x, pv.y - hv.y, pv.z - hv.z, pv.w - hv.w);
-            }
+            // (the R rows s_n * b_n were written by the gather warps' scaling pass; this team only adds the [v | t] block)
             fence_proxy_async_smem();
             team_bar<AW * 32>();                           // all 64 rows written
             if (awi == 0) {

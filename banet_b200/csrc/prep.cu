@@ -51,6 +51,29 @@ __global__ void grad_fixed_concat_kernel(const float* __restrict__ F, int nb, in
     }
 }
 
+// legacy/utils_python.py:61-117 `interpolate2d` / :177-232 `interpolate2d2`: bilinear with CLAMPED tap indices (:96-99) and, optionally, the
+// in-bounds mask (x == clip(x, 0, w-1)) & (y == clip(y, 0, h-1)) (:114-116).  Warp per point, lanes over channels.
+__global__ void interpolate2d_kernel(const float* __restrict__ data, const float* __restrict__ xy, float cs,
+                                     int nb, int h, int w, int C, int N, float* __restrict__ out, float* __restrict__ mask)
+{
+    const long long pt = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (pt >= (long long)nb * N) return;
+    const int b = (int)(pt / N);
+    const float x = xy[pt * 2] * cs, y = xy[pt * 2 + 1] * cs;
+    const float fx = floorf(x), fy = floorf(y);
+    const float dx = x - fx, dy = y - fy;
+    const bool fin = isfinite(x) && isfinite(y) && fabsf(x) < 1e9f && fabsf(y) < 1e9f;
+    const int xi = fin ? (int)fx : 0, yi = fin ? (int)fy : 0;
+    const int x0 = min(max(xi, 0), w - 1), x1 = min(max(xi + 1, 0), w - 1), y0 = min(max(yi, 0), h - 1), y1 = min(max(yi + 1, 0), h - 1);
+    const float w00 = (1.f - dx) * (1.f - dy), w01 = dx * (1.f - dy), w10 = (1.f - dx) * dy, w11 = dx * dy;
+    const float* img = data + (size_t)b * h * w * C;
+    const float *t00 = img + ((size_t)y0 * w + x0) * C, *t01 = img + ((size_t)y0 * w + x1) * C, *t10 = img + ((size_t)y1 * w + x0) * C, *t11 = img + ((size_t)y1 * w + x1) * C;
+    float* o = out + (size_t)pt * C;
+    for (int c = lane; c < C; c += 32) o[c] = w00 * __ldg(t00 + c) + w01 * __ldg(t01 + c) + w10 * __ldg(t10 + c) + w11 * __ldg(t11 + c);
+    if (mask && lane == 0) mask[pt] = (x >= 0.f && x <= (float)(w - 1) && y >= 0.f && y <= (float)(h - 1)) ? 1.f : 0.f;
+}
+
 // tf.contrib.resampler.resampler: bilinear, zero outside.  Warp per point, lanes over channels.
 __global__ void resample_kernel(const float* __restrict__ data, const float* __restrict__ xy, float cs,
                                 int nb, int h, int w, int C, int N, float* __restrict__ out)
@@ -243,6 +266,16 @@ extern "C" int banet_resample(const float* data, const float* xy, float coord_sc
     const long long thr = (long long)nb * N * 32;
     resample_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(data, xy, coord_scale, nb, h, w, C, N, out);
     BANET_CUDA_LAUNCH_CHECK("resample");
+    return BANET_OK;
+}
+
+extern "C" int banet_interpolate2d(const float* data, const float* xy, float coord_scale, int nb, int h, int w, int C, int N,
+                                   float* out, float* mask, banet_stream_t stream)
+{
+    BANET_REQUIRE(data && xy && out && nb > 0 && h > 0 && w > 0 && C > 0 && N > 0, BANET_ERR_BAD_ARG, "interpolate2d: bad argument");
+    const long long thr = (long long)nb * N * 32;
+    interpolate2d_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, (cudaStream_t)stream>>>(data, xy, coord_scale, nb, h, w, C, N, out, mask);
+    BANET_CUDA_LAUNCH_CHECK("interpolate2d");
     return BANET_OK;
 }
 

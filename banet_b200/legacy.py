@@ -61,7 +61,7 @@ class Tracker(torch.nn.Module):
         for level in range(1, 4):
             scale = 2 ** (3 - level)
             lay = layers[level - 1]
-            layer1 = ops.resample(lay[0:nb].contiguous(), points, 1.0 / scale)            # utils.interpolate2d2(layers[level-1][0:1], points/scale), :112
+            layer1 = ops.interpolate2d(lay[0:nb].contiguous(), points, 1.0 / scale)        # utils.interpolate2d2(layers[level-1][0:1], points/scale), :112
             layer2 = ops.grad_fixed_concat(lay[nb:2 * nb].contiguous())                     # :113-115
             levels.append(ops.Level(layer1, layer2, (k / scale).contiguous(), p, d, None))
             mlps.append(self.mlp_packed(str(level)))

@@ -128,6 +128,17 @@ def resample(data: Tensor, xy: Tensor, coord_scale: float = 1.0) -> Tensor:
     return out
 
 
+def interpolate2d(data: Tensor, xy: Tensor, coord_scale: float = 1.0, with_mask: bool = False):
+    """The legacy sampler (legacy/utils_python.py:61-117, 177-232): bilinear with clamped tap indices -> out [nb,N,C] (, mask [nb,N,1])."""
+    lib = load()
+    dt = _chk(data, "data"); nb, h, w, Cc = dt.shape
+    pts = _chk(xy, "xy"); N = pts.shape[1]
+    out = torch.empty(nb, N, Cc, device=dt.device, dtype=torch.float32)
+    mask = torch.empty(nb, N, 1, device=dt.device, dtype=torch.float32) if with_mask else None
+    check(lib.banet_interpolate2d(dt.data_ptr(), pts.data_ptr(), float(coord_scale), nb, h, w, Cc, N, out.data_ptr(), _ptr(mask), _stream()), "banet_interpolate2d")
+    return (out, mask) if with_mask else out
+
+
 def depth_compose(init_depth: Tensor, basis: Tensor, W: Tensor) -> Tensor:
     """init_depth [nb,M], basis [nb,M,K], W [nb,K,1] -> [nb,M]   (reference bundlenet.py:397)."""
     lib = load()

@@ -88,6 +88,11 @@ int banet_grad_fixed_concat(const float* F, int nb, int h, int w, int C, int swa
 int banet_resample(const float* data, const float* xy, float coord_scale, int nb, int h, int w, int C, int N,
                    float* out, banet_stream_t stream);
 
+/* The legacy sampler (legacy/utils_python.py:61-117 `interpolate2d`, :177-232 `interpolate2d2`): bilinear with CLAMPED tap indices;
+ * mask [nb,N] (optional, may be NULL) = the in-bounds test of :114-116.  Same layouts as banet_resample. */
+int banet_interpolate2d(const float* data, const float* xy, float coord_scale, int nb, int h, int w, int C, int N,
+                        float* out, float* mask, banet_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Layer level — one LM iteration = BundleNet.BundleIteration (bundlenet.py:193-278) or
  *     BundleNet.CameraIteration (:122-191) when K == 0 / B == NULL.

