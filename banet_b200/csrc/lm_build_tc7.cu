@@ -34,7 +34,7 @@ using namespace tc;
 
 constexpr int TILE = 64, W0 = 4, GW = 16, AW = 4, DW = 4;      // geometry | gather | algebra | drainer warps
 constexpr int THREADS = (W0 + GW + AW + DW) * 32;               // 896
-constexpr int KB = 128, NN = 160;
+constexpr int NN = 160;
 constexpr int STAGE_A = 4 * TILE * 128, STAGE_R = 5 * TILE * 128;
 constexpr int REC = 16;
 constexpr int CHAIN = 8, TMEM_COLS = 512, ACCL = 320;
@@ -162,7 +162,6 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
 {
     using SM = Smem<MODE, NCH>;
     constexpr int NST = SM::NST, NREC = SM::NREC, NWB = SM::NWB;
-    constexpr bool FLY = true;
     constexpr int KR = 32 * KBLK, EXTB = KBLK, NMMA = KBLK == 4 ? NN : KR + 16;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // align through the 32-bit shared address so that the compiler keeps every access in the shared state space (LDS/STS, not generic LD/ST)
