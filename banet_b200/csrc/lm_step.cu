@@ -8,10 +8,11 @@
 //      lanes over consecutive outputs (coalesced 128-B weight rows, 8 rows in flight per lane), slices combined through shared memory;
 //      lambda = base * ||rbar||^(2 + tanh(.))                                                            (bundlenet.py:243-253)
 //   2. packed lower triangle of H (+ damping on the diagonal) and g as row P of the same packed array, in S = double (P <= 200) or float;
-//   3. right-looking Cholesky in panels of 8 columns: thread 0 factors the 8x8 diagonal block, one thread per row solves the panel rows
-//      (row P = the right-hand side: forward substitution comes for free), warp-per-row trailing update: 3 block barriers per panel instead
-//      of one per column;
-//   4. back substitution L^T x = y panel by panel (8 warps form the 8 dot products of a panel, thread 0 solves the 8x8 triangle);
+//   3. right-looking Cholesky in panels of 4 columns: one thread per row of the panel (the block's own rows, the rows below, and row P = the
+//      right-hand side, so that forward substitution comes for free); every row owner factors the 4x4 diagonal block redundantly IN REGISTERS and
+//      solves its own row against it (a single thread factoring through shared memory was 37 % of the first version's run time, measured);
+//      warp-per-row trailing update; 3 block barriers per panel instead of one per column;
+//   4. back substitution L^T x = y panel by panel (4 warps form the 4 dot products of a panel, thread 0 solves the 4x4 triangle in registers);
 //   5. delta, W' = W + delta_d, status; R' = exp(w) R, T' = V(w) t + exp(w) T in double by thread 0 (per-pair VMatrix).
 // The reference's batch-interleaved VMatrix (vmatrix_batch_scramble, bundlenet.py:45) needs every pair's delta first: the host falls back to
 // the three-kernel path for that option.
@@ -22,7 +23,7 @@ namespace banet {
 
 constexpr int STEP_THREADS = 1024;
 constexpr int STEP_WARPS = STEP_THREADS / 32;
-constexpr int STEP_NB = 8;                       // Cholesky panel width
+constexpr int STEP_NB = 4;                       // Cholesky panel width (the panel owners keep the NB x NB block in registers: 1024 threads leave 64 registers each)
 
 __device__ __forceinline__ float selu_s(float x) {
     const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
@@ -46,6 +47,15 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ in, const 
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         if (j < cout) {
             int i = i0;
+            for (; i + 15 < i1; i += 16) {                       // 16 weight rows in flight per lane (the loop is pure L2 latency)
+                float wv[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) wv[u] = __ldg(Wm + (size_t)(i + u) * cout + j);
+#pragma unroll
+                for (int u = 0; u < 16; u += 4) {
+                    a0 = fmaf(in[i + u], wv[u], a0); a1 = fmaf(in[i + u + 1], wv[u + 1], a1); a2 = fmaf(in[i + u + 2], wv[u + 2], a2); a3 = fmaf(in[i + u + 3], wv[u + 3], a3);
+                }
+            }
             for (; i + 7 < i1; i += 8) {
                 const float w0 = __ldg(Wm + (size_t)i * cout + j), w1 = __ldg(Wm + (size_t)(i + 1) * cout + j), w2 = __ldg(Wm + (size_t)(i + 2) * cout + j),
                             w3 = __ldg(Wm + (size_t)(i + 3) * cout + j), w4 = __ldg(Wm + (size_t)(i + 4) * cout + j), w5 = __ldg(Wm + (size_t)(i + 5) * cout + j),
@@ -65,7 +75,7 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ in, const 
     __syncthreads();
 }
 
-template <typename S>
+template <typename S, bool FULL>
 __global__ void __launch_bounds__(STEP_THREADS)
 lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const float* __restrict__ rbar_sum, int N, int C,
                const float* __restrict__ mlp, float base, const float* __restrict__ lambda_in, const StepMode mode, const float* __restrict__ nvalid,
@@ -75,10 +85,15 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
                float* __restrict__ delta, float* __restrict__ lambda_out, int32_t* __restrict__ status, int status_accumulate)
 {
     extern __shared__ __align__(16) unsigned char smraw[];
-    S* A = reinterpret_cast<S*>(smraw);                              // packed lower triangle, rows 0..P (row P = right-hand side)
-    const size_t nA = (size_t)(P + 1) * (P + 2) / 2;
+    // lower triangle of the damped matrix, rows 0..P (row P = right-hand side).  FULL: square storage with an odd row pitch (column walks over
+    // consecutive rows are bank-conflict free for 64-bit words; the packed triangle's varying row offsets were 2..4-way conflicted); else packed.
+    S* A = reinterpret_cast<S*>(smraw);
+    const int LD = (P + 1) | 1;
+    const size_t nA = FULL ? (size_t)(P + 1) * LD : (size_t)(P + 1) * (P + 2) / 2;
+    auto IX = [&](int i, int k) -> int { return FULL ? i * LD + k : i * (i + 1) / 2 + k; };
     S* xs = A + nA;                                                  // [P] solution
-    S* dots = xs + P;                                                // [STEP_NB]
+    S* dinv = xs + P;                                                // [P] reciprocals of the Cholesky diagonal
+    S* dots = dinv + P;                                              // [STEP_NB]
     float* mbuf = reinterpret_cast<float*>(dots + STEP_NB);          // MLP buffers: 3 x 4C floats
     __shared__ int s_flag;
     __shared__ float s_norm2, s_lam;
@@ -127,9 +142,9 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
             if (!isfinite(v)) bad = 1;
             S sv = (S)v;
             if (k == i && i < ndamped) sv += ((S)v + (S)eps) * (S)lam;
-            A[tri3(i, k)] = sv;
+            A[IX(i, k)] = sv;
         }
-    for (int k = tid; k < P; k += STEP_THREADS) { const float v = g[(size_t)b * P + k]; if (!isfinite(v)) bad = 1; A[tri3(P, k)] = (S)v; }
+    for (int k = tid; k < P; k += STEP_THREADS) { const float v = g[(size_t)b * P + k]; if (!isfinite(v)) bad = 1; A[IX(P, k)] = (S)v; }
     if (!isfinite(lam)) bad = 1;
     if (bad) atomicOr(&s_flag, 2);
     __syncthreads();
@@ -137,52 +152,86 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
     // ---- 3. blocked Cholesky; row P rides along: afterwards A[P][:] = y = L^-1 g ----------------------------------------------------------------
     for (int j0 = 0; j0 < P; j0 += STEP_NB) {
         const int jb = min(STEP_NB, P - j0);
-        if (tid == 0) {                                              // 8x8 diagonal block, in place
-            for (int c = 0; c < jb; ++c) {
-                S d = A[tri3(j0 + c, j0 + c)];
-                for (int m = 0; m < c; ++m) { const S l = A[tri3(j0 + c, j0 + m)]; d -= l * l; }
-                if (!(d > (S)0)) { s_flag |= 1; d = (S)1; }
-                const S ld = sqrt(d);
-                A[tri3(j0 + c, j0 + c)] = ld;
-                const S inv = (S)1 / ld;
-                for (int r = c + 1; r < jb; ++r) {
-                    S v = A[tri3(j0 + r, j0 + c)];
-                    for (int m = 0; m < c; ++m) v -= A[tri3(j0 + r, j0 + m)] * A[tri3(j0 + c, j0 + m)];
-                    A[tri3(j0 + r, j0 + c)] = v * inv;
-                }
+        // Panel: thread t owns row j0 + t (the block's own rows first, then the rows below, then the rhs row P).  EVERY owner factors the 8x8 diagonal
+        // block redundantly in registers (36 independent loads, then a register-only chain) instead of waiting for one thread to do it through
+        // shared memory (measured: that serial section and its barrier were 37 % of the kernel), then solves its own row against it.
+        {
+            const int i = j0 + tid;
+            const bool owner = i <= P;
+            S L[STEP_NB][STEP_NB], row[STEP_NB], Linv[STEP_NB];
+            if (owner) {
+#pragma unroll
+                for (int r = 0; r < STEP_NB; ++r)
+#pragma unroll
+                    for (int c = 0; c < STEP_NB; ++c) L[r][c] = (c <= r && r < jb) ? A[IX(j0 + r, j0 + c)] : (S)(r == c ? 1 : 0);
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) row[c] = (c < jb && (tid >= jb || c <= tid)) ? A[IX(i, j0 + c)] : (S)0;
             }
-        }
-        __syncthreads();
-        {                                                            // panel rows: L21[i][:] = A21[i][:] L11^-T, one thread per row (incl. row P)
-            const int i = j0 + jb + tid;
-            if (i <= P) {
-                S row[STEP_NB];
+            __syncthreads();                                         // every owner has read the block before its rows are overwritten
+            if (owner) {
+                bool notpd = false;
 #pragma unroll
-                for (int c = 0; c < STEP_NB; ++c) row[c] = (c < jb) ? A[tri3(i, j0 + c)] : (S)0;
+                for (int c = 0; c < STEP_NB; ++c) {                  // unblocked Cholesky of the block, registers only
+                    S d = L[c][c];
 #pragma unroll
-                for (int c = 0; c < STEP_NB; ++c) {
-                    if (c < jb) {
-                        S v = row[c];
+                    for (int m = 0; m < STEP_NB; ++m) if (m < c) d -= L[c][m] * L[c][m];
+                    if (c < jb && !(d > (S)0)) { notpd = true; d = (S)1; }
+                    const S inv = rsqrt(d), ld = d * inv;                // one reciprocal square root per column; no divisions anywhere on the path
+                    L[c][c] = ld; Linv[c] = inv;
 #pragma unroll
-                        for (int m = 0; m < STEP_NB; ++m) if (m < c) v -= row[m] * A[tri3(j0 + c, j0 + m)];
-                        row[c] = v / A[tri3(j0 + c, j0 + c)];
+                    for (int r = 0; r < STEP_NB; ++r) {
+                        if (r > c) {
+                            S v = L[r][c];
+#pragma unroll
+                            for (int m = 0; m < STEP_NB; ++m) if (m < c) v -= L[r][m] * L[c][m];
+                            L[r][c] = v * inv;
+                        }
                     }
                 }
+                if (tid == 0 && notpd) s_flag |= 1;
+                if (tid < jb) {                                      // a block row: its part of the factor
 #pragma unroll
-                for (int c = 0; c < STEP_NB; ++c) if (c < jb) A[tri3(i, j0 + c)] = row[c];
+                    for (int c = 0; c < STEP_NB; ++c) if (c <= tid) { S v = (S)0;
+#pragma unroll
+                        for (int r = 0; r < STEP_NB; ++r) if (r == tid) v = L[r][c];
+                        A[IX(i, j0 + c)] = v; }
+#pragma unroll
+                    for (int c = 0; c < STEP_NB; ++c) if (c == tid) dinv[j0 + c] = Linv[c];
+                } else {                                             // a row below (or the rhs row): L21[i][:] = A21[i][:] L11^-T
+#pragma unroll
+                    for (int c = 0; c < STEP_NB; ++c) {
+                        if (c < jb) {
+                            S v = row[c];
+#pragma unroll
+                            for (int m = 0; m < STEP_NB; ++m) if (m < c) v -= row[m] * L[c][m];
+                            row[c] = v * Linv[c];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < STEP_NB; ++c) if (c < jb) A[IX(i, j0 + c)] = row[c];
+                }
             }
         }
         __syncthreads();
         for (int i = j0 + jb + warp; i <= P; i += STEP_WARPS) {      // trailing update, warp per row, lanes over columns
             S li[STEP_NB];
 #pragma unroll
-            for (int c = 0; c < STEP_NB; ++c) li[c] = (c < jb) ? A[tri3(i, j0 + c)] : (S)0;
+            for (int c = 0; c < STEP_NB; ++c) li[c] = (c < jb) ? A[IX(i, j0 + c)] : (S)0;
             const int kend = (i == P) ? P - 1 : i;
-            for (int k = j0 + jb + lane; k <= kend; k += 32) {
-                S s = (S)0;
+            for (int k0 = j0 + jb; k0 <= kend; k0 += 128) {         // 4 independent column chunks in flight (no store between their loads)
+                S sacc[4];
 #pragma unroll
-                for (int c = 0; c < STEP_NB; ++c) if (c < jb) s += li[c] * A[tri3(k, j0 + c)];
-                A[tri3(i, k)] -= s;
+                for (int q = 0; q < 4; ++q) {
+                    const int k = k0 + 32 * q + lane;
+                    S sv = (S)0;
+                    if (k <= kend) {
+#pragma unroll
+                        for (int c = 0; c < STEP_NB; ++c) if (c < jb) sv += li[c] * A[IX(k, j0 + c)];
+                    }
+                    sacc[q] = sv;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int k = k0 + 32 * q + lane; if (k <= kend) A[IX(i, k)] -= sacc[q]; }
             }
         }
         __syncthreads();
@@ -194,18 +243,29 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         const int j0 = pnl * STEP_NB, jb = min(STEP_NB, P - j0);
         if (warp < jb) {                                             // dots[c] = sum_{i >= j0+jb} L[i][j0+c] x[i]
             S s = (S)0;
-            for (int i = j0 + jb + lane; i < P; i += 32) s += A[tri3(i, j0 + warp)] * xs[i];
+            for (int i = j0 + jb + lane; i < P; i += 32) s += A[IX(i, j0 + warp)] * xs[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) dots[warp] = s;
         }
         __syncthreads();
-        if (tid == 0) {
-            for (int c = jb - 1; c >= 0; --c) {
-                S v = A[tri3(P, j0 + c)] - dots[c];
-                for (int m = c + 1; m < jb; ++m) v -= A[tri3(j0 + m, j0 + c)] * xs[j0 + m];
-                xs[j0 + c] = v / A[tri3(j0 + c, j0 + c)];
+        if (tid == 0) {                                              // 8x8 triangle in registers (independent loads first)
+            S L[STEP_NB][STEP_NB], y[STEP_NB], x[STEP_NB];
+#pragma unroll
+            for (int r = 0; r < STEP_NB; ++r)
+#pragma unroll
+                for (int c = 0; c < STEP_NB; ++c) L[r][c] = (c <= r && r < jb) ? A[IX(j0 + r, j0 + c)] : (S)(r == c ? 1 : 0);
+#pragma unroll
+            for (int c = 0; c < STEP_NB; ++c) y[c] = (c < jb) ? A[IX(P, j0 + c)] - dots[c] : (S)0;
+#pragma unroll
+            for (int c = STEP_NB - 1; c >= 0; --c) {
+                S v = y[c];
+#pragma unroll
+                for (int m = 0; m < STEP_NB; ++m) if (m > c) v -= L[m][c] * x[m];
+                x[c] = v * (c < jb ? dinv[j0 + c] : (S)1);
             }
+#pragma unroll
+            for (int c = 0; c < STEP_NB; ++c) if (c < jb) xs[j0 + c] = x[c];
         }
         __syncthreads();
     }
@@ -250,13 +310,13 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
     }
 }
 
-size_t lm_step_smem(int P, int C, bool use_double)
+size_t lm_step_smem(int P, int C, bool use_double, bool full)
 {
-    const size_t nA = (size_t)(P + 1) * (P + 2) / 2 + P + STEP_NB;
+    const size_t nA = (full ? (size_t)(P + 1) * ((P + 1) | 1) : (size_t)(P + 1) * (P + 2) / 2) + 2 * (size_t)P + STEP_NB;
     return nA * (use_double ? sizeof(double) : sizeof(float)) + (size_t)12 * C * sizeof(float);
 }
 
-bool lm_step_supported(int P, int C) { return lm_step_smem(P, C, false) <= 220 * 1024; }
+bool lm_step_supported(int P, int C) { return lm_step_smem(P, C, false, false) <= 220 * 1024; }
 
 // lambda_in != nullptr: used as is; else lambda = base * ||rbar||^(exp0 + MLP(rbar)) (MLP term 0 when mlp == nullptr).
 // In-place R/T/W (R_out == R ...) is fine: a pair's CTA reads before it writes.
@@ -266,21 +326,23 @@ int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N
 {
     const int P = 6 + K;
     const int ndamped = opts.undamped_last ? P - 1 : P;
-    const bool use_double = lm_step_smem(P, C, true) <= 200 * 1024;
-    const size_t smem = lm_step_smem(P, C, use_double);
+    // storage: square double (P <= ~150), packed double (P <= ~200), packed float beyond
+    const bool full = lm_step_smem(P, C, true, true) <= 200 * 1024;
+    const bool use_double = full || lm_step_smem(P, C, true, false) <= 200 * 1024;
+    const size_t smem = lm_step_smem(P, C, use_double, full);
     BANET_REQUIRE(smem <= 220 * 1024, BANET_ERR_UNSUPPORTED, "lm_step: P=%d, C=%d do not fit shared memory", P, C);
-    cudaError_t e;
-    if (use_double) {
-        e = cudaFuncSetAttribute(lm_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto launch = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-        lm_step_kernel<double><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, mode, nvalid, P, opts.damping_eps, ndamped, R, T, W,
-                                                               R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
-    } else {
-        e = cudaFuncSetAttribute(lm_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("lm_step smem attr: %s", cudaGetErrorString(e)); return BANET_ERR_CUDA; }
-        lm_step_kernel<float><<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, mode, nvalid, P, opts.damping_eps, ndamped, R, T, W,
-                                                              R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
-    }
+        kern<<<nb, STEP_THREADS, smem, st>>>(H, g, rbar_sum, N, C, mlp, base, lambda_in, mode, nvalid, P, opts.damping_eps, ndamped, R, T, W,
+                                             R_out, T_out, W_out, delta, lambda_out, status, status_accumulate);
+        return BANET_OK;
+    };
+    int rc;
+    if (full) rc = launch(lm_step_kernel<double, true>);
+    else if (use_double) rc = launch(lm_step_kernel<double, false>);
+    else rc = launch(lm_step_kernel<float, false>);
+    if (rc) return rc;
     BANET_CUDA_LAUNCH_CHECK("lm_step_kernel launch");
     return BANET_OK;
 }

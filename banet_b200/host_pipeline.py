@@ -133,8 +133,10 @@ class ResizeHostSolver:
         self.nimg = int(basis.shape[0]); self.half = self.nimg // 2
         if self.nimg % 2:
             raise ValueError("the half-swap pairing of bundlenet.py:386 needs an even batch")
+        # chunk order: (pairs a..b of the first half) then (the same image set in the other direction, pairs a+half..b+half): both read images
+        # a..b and a+half..b+half, so each image set is copied once and two chunks of compute follow it; the copies of the next set overlap them
         per_half = max(1, int(chunks) // 2)
-        self.ranges = [(o + a, o + b) for o in (0, self.half) for a, b in chunk_ranges(self.half, per_half)]
+        self.ranges = [(o + a, o + b) for a, b in chunk_ranges(self.half, per_half) for o in (0, self.half)]
         self.copy_stream = torch.cuda.Stream(self.dev); self.compute_stream = torch.cuda.Stream(self.dev)
         dev = self.dev
         self.d_layers = [torch.empty(t.shape, dtype=torch.float32, device=dev) for t in self.h_layers]

@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-chunks", type=int, default=4, help="pair chunks of the host pipeline (copy of chunk k+1 overlaps the solve of chunk k)")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="pair chunks of the host pipeline (copy of chunk k+1 overlaps the solve of chunk k)")
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
