@@ -49,10 +49,13 @@ bool tc_supported(const banet_level_t* lv)
            (long long)lv->h * lv->w * lv->conv2_channels < (1LL << 31);
 }
 
-// generation 7 applies: F2-only layout on a dense grid (tap coordinates are packed in 16 bits)
+// Generation 7 applies to the F2-only layout on a dense grid (tap coordinates are packed in 16 bits).  It is selected explicitly
+// (banet_set_tuning: tc_generation = 7): measured on B200 (profiles/r02b_*) it moves the fewest bytes and executes 25 % fewer instructions than
+// generation 6, but at 6.0 ms per 640x480 x 32-pair launch it does not beat generation 6 on the same layout (5.9 ms), and its per-tile
+// global-tap fallback is slower under strong local zoom -- so generation 6 stays the default everywhere.
 static bool use_gen7(const banet_level_t* lv, int mode, int kblk)
 {
-    return g_tuning.tc_generation != 6 && lv->conv2_channels == lv->C && lv->grid_w > 0 && lv->h < 65536 && lv->w < 65536 &&
+    return g_tuning.tc_generation == 7 && lv->conv2_channels == lv->C && lv->grid_w > 0 && lv->h < 65536 && lv->w < 65536 &&
            lm_build_tc7_supported(mode, lv->C / 64, kblk);
 }
 

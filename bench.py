@@ -425,7 +425,7 @@ def main():
     top = per_level[-1]
     # DRAM traffic of the dominant kernel per launch: from the committed ncu capture of THIS kernel / layout (profiles/lm_build_traffic.json,
     # stamped with the commit and configuration it was taken on); null when the capture is of another kernel or layout
-    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else ("lm_build_tc7_kernel" if args.layout == "f2" else "lm_build_tc6_kernel")
+    kname = "lm_build_kernel" if PREC == _lib.PREC_FP32_SIMT else "lm_build_tc6_kernel"
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "lm_build_traffic.json")
     if os.path.exists(tpath):

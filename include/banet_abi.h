@@ -44,7 +44,7 @@ int         banet_num_sms(void);
 /* Diagnostic / test knobs (process-wide; defaults = production).  Results never depend on them beyond
  * fp32 summation order. */
 typedef struct banet_tuning {
-    int tc_generation;      /* 0: newest tensor-core build kernel that applies (7: TMA-staged F2 windows, else 6); 6: force generation 6 */
+    int tc_generation;      /* 0 or 6: generation 6 (ld.global taps; the default: fastest measured); 7: TMA-staged F2 windows where they apply (F2-only layout + dense grid) */
     int tc7_force_direct;   /* 1: generation 7 takes its per-tile global-tap fallback for every tile (tests the fallback) */
     int tc7_band_rows;      /* generation 7 walks the 8x8 tiles of a pair in bands of this many tile rows (L2 reuse of the window halos); default 4 */
 } banet_tuning_t;

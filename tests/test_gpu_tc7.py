@@ -31,7 +31,7 @@ def _f2_level(ops, lv, grid=True):
 @pytest.mark.parametrize("prec", [1, 2])
 def test_tc7_matches_oracle(prec, C):
     """Small dense level (ragged 8x8 edge tiles: 44x52) against the float64 oracle's block form."""
-    from banet_b200 import ops
+    from banet_b200 import ops, _lib
     sc = _scene(3, 44, 52, C, seed=70 + C, device="cpu")
     lv = sc.levels[0]
     Wt = sc.W0 + 0.01 * torch.randn(sc.W0.shape, generator=torch.Generator().manual_seed(2))
@@ -39,6 +39,7 @@ def test_tc7_matches_oracle(prec, C):
     rH, rg, rrbar, rnv = O.normal_equations_structured(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"],
                                                        sc.R0.double(), sc.T0.double(), Wt.double())
     L = ops.Level(to_cuda32(lv.conv1), to_cuda32(lv.conv2[..., :C]), to_cuda32(lv.intr), to_cuda32(lv.p), to_cuda32(lv.D), to_cuda32(lv.B), grid=lv.grid)
+    _lib.set_tuning(tc_generation=7)
     H, g, rbar, nv = ops.lm_build(L, to_cuda32(sc.R0), to_cuda32(sc.T0), to_cuda32(Wt), precision=prec)
     tol = {1: 2e-4, 2: 2e-5}[prec]       # N = 2288 points per pair: tf32 rounding of H averages out as 1/sqrt(N)
     print(f"prec={prec} C={C}: relH {rel_fro(H, rH):.2e} relg {rel_fro(g, rg.squeeze(-1)):.2e}")
