@@ -1,7 +1,8 @@
 """GPU: the SHIPPED default precision policy, whole solves, against the float64 oracle at the north-star tolerance.
 
-cfg2-shaped case (BASELINE.json configs[1] with nb reduced to 1 so that the float64 oracle finishes in about two minutes of host time; the
-nb = 2 run of the same case is recorded in profiles/r02a_precision_vs_oracle_cfg2shape.txt): 4 dense levels 80x60 .. 640x480,
+cfg2-shaped case, sized so that the float64 oracle finishes in about a minute of host time on the GPU box (the full-resolution nb = 2 run of
+BASELINE.json configs[1] -- 4 levels up to 640x480, 400 s of oracle time -- is recorded in profiles/r02a_precision_vs_oracle_cfg2shape.txt):
+nb = 1, 4 dense levels 40x30 .. 320x240 (the finest level is above the 65536-point threshold of the level-wise policy, so both TF32X3 and TF32X1 run),
 C = K = 128, lambda-MLP in the loop, 5 LM iterations per level; both conv2 layouts (the reference's [F2|gx|gy] -> generation-6 kernel,
 F2-only -> generation 7).  Asserted at 1e-4 rel-fro on R, T, W and the depth output D + B.W (bundlenet.py:397) for AUTO (what
 bench.py times) and for the fp32-grade modes; the other modes are printed."""
@@ -18,8 +19,8 @@ TOL = 1e-4
 def cfg2_case():
     from banet_b200 import ops, synth
     nb = 1
-    torch.set_num_threads(min(32, max(1, len(__import__("os").sched_getaffinity(0)))))      # the float64 oracle is memory-bound: more threads only thrash
-    sc = synth.make_scene(nb=nb, H=480, W=640, C=128, K=128, level_ids=(0, 1, 2, 3), seed=1236, device="cuda", dtype=torch.float32)
+    torch.set_num_threads(max(1, len(__import__("os").sched_getaffinity(0))))
+    sc = synth.make_scene(nb=nb, H=240, W=320, C=128, K=128, level_ids=(0, 1, 2, 3), seed=1236, device="cuda", dtype=torch.float32)
     mlps = [O.init_lambda_mlp(128, seed=7 + l.level, dtype=torch.float32) for l in sc.levels]
     olv = []
     for l, m in zip(sc.levels, mlps):
