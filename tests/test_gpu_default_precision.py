@@ -19,7 +19,6 @@ TOL = 1e-4
 def cfg2_case():
     from banet_b200 import ops, synth
     nb = 1
-    torch.set_num_threads(max(1, len(__import__("os").sched_getaffinity(0))))
     sc = synth.make_scene(nb=nb, H=240, W=320, C=128, K=128, level_ids=(0, 1, 2, 3), seed=1236, device="cuda", dtype=torch.float32)
     mlps = [O.init_lambda_mlp(128, seed=7 + l.level, dtype=torch.float32) for l in sc.levels]
     olv = []
