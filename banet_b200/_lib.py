@@ -34,7 +34,8 @@ class BanetSolveOpts(C.Structure):
 
 class BanetTuning(C.Structure):
     """struct banet_tuning (include/banet_abi.h): diagnostic knobs, defaults = production."""
-    _fields_ = [("tc_generation", C.c_int), ("tc7_force_direct", C.c_int), ("tc7_band_rows", C.c_int)]
+    _fields_ = [("tc_generation", C.c_int), ("tc7_force_direct", C.c_int), ("tc7_band_rows", C.c_int),
+                ("tc6_band_rows", C.c_int), ("tc6_l2_hints", C.c_int), ("tc6_tap_prefetch", C.c_int)]
 
 
 class BanetLegacyOpts(C.Structure):
@@ -113,9 +114,10 @@ def check(rc: int, what: str) -> None:
         raise BanetError(f"{what} failed (code {rc}): {msg}")
 
 
-def set_tuning(tc_generation: int = 0, tc7_force_direct: bool = False, tc7_band_rows: int = 4) -> None:
+def set_tuning(tc_generation: int = 0, tc7_force_direct: bool = False, tc7_band_rows: int = 4, tc6_band_rows: int = 0,
+               tc6_l2_hints: int = 0, tc6_tap_prefetch: int = 0) -> None:
     """Diagnostic knobs (process-wide); call with no arguments to restore the production defaults."""
-    t = BanetTuning(int(tc_generation), int(tc7_force_direct), int(tc7_band_rows))
+    t = BanetTuning(int(tc_generation), int(tc7_force_direct), int(tc7_band_rows), int(tc6_band_rows), int(tc6_l2_hints), int(tc6_tap_prefetch))
     check(load().banet_set_tuning(C.byref(t)), "banet_set_tuning")
 
 

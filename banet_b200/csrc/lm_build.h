@@ -12,7 +12,9 @@ struct BuildParams {
     long long total_tiles;
     int grid_w, grid_h, tiles_x, tiles_y;   // dense-grid 8x8 tiling (tensor-core path); grid_w == 0 -> linear 64-pixel tiles
     int kq_i, kq_j;                   // fp32 SIMT path, K > 128: the 128 x 128 block of H_dd this launch computes
-    int band_rows;                    // generation 7: tiles are walked in bands of this many tile rows, column by column inside a band
+    int band_rows;                    // dense-grid tensor-core kernels: tiles are walked in bands of this many tile rows, column by column inside a band
+    int tap_prefetch;                 // generation 6: 0 off, 1 the geometry warps prefetch the tap footprint into L2 (halo from the tile's border pixels), 2 = every pixel also fetches its lower row
+    int l2_hints;                     // generation 6: 0 none, 1 read-once streams evict-first, 2 = 1 + taps evict-last
     int hdd_transposed;               // tensor-core path stores the H_dd block of a slot column-major (coalesced TMEM drains)
     int force_direct;                 // generation 7, testing: take the global-tap fallback for every tile
     long long* trace;                 // optional debug timeline buffer (NULL in production)

@@ -81,7 +81,15 @@ __device__ __forceinline__ TileCoord tile_coord(const BuildParams& prm, long lon
     const unsigned t = (unsigned)tl, tpp = (unsigned)prm.tiles_per_pair;
     tc.b = (int)(t / tpp);
     const int r = (int)(t - (unsigned)tc.b * tpp);
-    if (prm.grid_w > 0) { const int tyi = r / prm.tiles_x; tc.ty0 = tyi * 8; tc.tx0 = (r - tyi * prm.tiles_x) * 8; tc.n0 = 0; tc.cnt = TILE; }
+    if (prm.grid_w > 0) {
+        int tyi, txi;
+        if (prm.band_rows > 1) {        // bands of band_rows tile rows, column by column inside a band: vertically adjacent tiles follow each other
+            const int bsz = prm.tiles_x * prm.band_rows, band = r / bsz, rem = r - band * bsz;
+            const int rows = min(prm.band_rows, prm.tiles_y - band * prm.band_rows);
+            txi = rem / rows; tyi = band * prm.band_rows + (rem - txi * rows);
+        } else { tyi = r / prm.tiles_x; txi = r - tyi * prm.tiles_x; }
+        tc.ty0 = tyi * 8; tc.tx0 = txi * 8; tc.n0 = 0; tc.cnt = TILE;
+    }
     else { tc.n0 = r * TILE; tc.cnt = min(TILE, prm.N - tc.n0); tc.tx0 = tc.ty0 = 0; }
     return tc;
 }
@@ -165,6 +173,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         for (int j = 0; j < ntiles; ++j) {
             const TileCoord tc = nxt;
             if (++nxt_r == prm.tiles_per_pair) { nxt_r = 0; ++nxt.b; nxt.tx0 = 0; nxt.ty0 = 0; nxt.n0 = 0; nxt.cnt = grid2d ? TILE : min(TILE, N); }
+            else if (grid2d && prm.band_rows > 1) nxt = tile_coord(prm, t_begin + j + 1);
             else if (grid2d) { nxt.tx0 += 8; if (nxt.tx0 >= prm.tiles_x * 8) { nxt.tx0 = 0; nxt.ty0 += 8; } }
             else { nxt.n0 += TILE; nxt.cnt = min(TILE, N - nxt.n0); }
             const int b = tc.b;
@@ -285,6 +294,33 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     o[0] = (uint32_t)((y0 * w + x0) * c2); o[1] = (uint32_t)((y0 * w + x1) * c2);
                     o[2] = (uint32_t)((y1 * w + x0) * c2); o[3] = (uint32_t)((y1 * w + x1) * c2);
                 }
+                if (prm.tap_prefetch && mask != 0.f) {
+                    // pull this pixel's share of the tile's tap footprint into L2 one to two tiles before the gather warps load it: the gather is
+                    // bound by the latency of its 13 dependent-free loads, not by their count.  Interior pixels fetch their (x0, y0) texel only;
+                    // the tile's border pixels add the halo, so that under a near-unit warp every texel is requested about once.
+                    const float* imgp = prm.conv2 + (size_t)b * h * w * c2;
+                    const int px = nlr & 7, py = nlr >> 3;
+                    const bool edge_x = !grid2d || px == 7, edge_y = !grid2d || py == 7 || prm.tap_prefetch == 2;
+                    if constexpr (!FLY) {
+                        const uint32_t by = (uint32_t)c2 * 4u;
+                        prefetch_l2_bulk(imgp + o[0], by);
+                        if (edge_x && o[1] != o[0]) prefetch_l2_bulk(imgp + o[1], by);
+                        if (edge_y && o[2] != o[0]) {
+                            prefetch_l2_bulk(imgp + o[2], by);
+                            if (edge_x && o[3] != o[2]) prefetch_l2_bulk(imgp + o[3], by);
+                        }
+                    } else {
+                        const bool first_x = !grid2d || px == 0, first_y = !grid2d || py == 0;
+                        const int xs = max(x0 - (first_x ? 1 : 0), 0), xe = min(x0 + (edge_x ? 2 : 0), w - 1);
+                        const uint32_t by = (uint32_t)(xe - xs + 1) * (uint32_t)c2 * 4u;
+                        prefetch_l2_bulk(imgp + ((size_t)y0 * w + xs) * c2, by);
+                        if (first_y && y0 > 0) prefetch_l2_bulk(imgp + ((size_t)(y0 - 1) * w + xs) * c2, by);
+                        if (edge_y) {
+                            if (y0 + 1 < h) prefetch_l2_bulk(imgp + ((size_t)(y0 + 1) * w + xs) * c2, by);
+                            if (y0 + 2 < h) prefetch_l2_bulk(imgp + ((size_t)(y0 + 2) * w + xs) * c2, by);
+                        }
+                    }
+                }
                 float* rec = sRec + (sr * TILE + nlr) * REC;
                 *reinterpret_cast<uint4*>(rec) = make_uint4(o[0], o[1], o[2], o[3]);
                 *reinterpret_cast<float4*>(rec + 4) = make_float4(mask, x, y, iZ);
@@ -308,6 +344,9 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         float4 tb[13];
         float m11 = 0.f, m12 = 0.f, m22 = 0.f, q1 = 0.f, q2 = 0.f;
         int cur_b = -1, ndump = 0;
+        // L2 policy: conv1 is read exactly once (evict-first), the taps are what neighbouring tiles re-read
+        const uint64_t pol_stream = prm.l2_hints >= 1 ? l2_policy_evict_first() : l2_policy_evict_normal();
+        const uint64_t pol_tap = prm.l2_hints >= 2 ? l2_policy_evict_last() : l2_policy_evict_normal();
 
         auto dump_rb = [&]() {
             if (ndump > 0) mbar_wait_parked(rbfree, (ndump - 1) & 1);       // the algebra warps consumed the previous hand-over
@@ -343,19 +382,20 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                     const uint4 o = *reinterpret_cast<const uint4*>(rec + pl * REC);
                     const int n = __float_as_int(rec[pl * REC + 11]);
                     const float* img = imgb + co;
-                    tb[0] = ld_stream_f4(c1b + (size_t)n * C + co);
+                    auto ldt = [&](const float* q) { return ldg4_hint(q, pol_tap); };
+                    tb[0] = ld_stream_f4_hint(c1b + (size_t)n * C + co, pol_stream);
                     if constexpr (!FLY) {
                         const float* t00 = img + o.x; const float* t01 = img + o.y; const float* t10 = img + o.z; const float* t11 = img + o.w;
-                        tb[1] = ldg4(t00); tb[2] = ldg4(t01); tb[3] = ldg4(t10); tb[4] = ldg4(t11);
-                        tb[5] = ldg4(t00 + C); tb[6] = ldg4(t01 + C); tb[7] = ldg4(t10 + C); tb[8] = ldg4(t11 + C);
-                        tb[9] = ldg4(t00 + 2 * C); tb[10] = ldg4(t01 + 2 * C); tb[11] = ldg4(t10 + 2 * C); tb[12] = ldg4(t11 + 2 * C);
+                        tb[1] = ldt(t00); tb[2] = ldt(t01); tb[3] = ldt(t10); tb[4] = ldt(t11);
+                        tb[5] = ldt(t00 + C); tb[6] = ldt(t01 + C); tb[7] = ldt(t10 + C); tb[8] = ldt(t11 + C);
+                        tb[9] = ldt(t00 + 2 * C); tb[10] = ldt(t01 + 2 * C); tb[11] = ldt(t10 + 2 * C); tb[12] = ldt(t11 + 2 * C);
                     } else {
                         const uint2 cxy = *reinterpret_cast<const uint2*>(rec + pl * REC + 14);
                         const float* rm = img + o.x; const float* r0 = img + o.y; const float* r1 = img + o.z; const float* rp = img + o.w;
                         const uint32_t oM = (cxy.x & 0xffffu) * c2, o0 = (cxy.x >> 16) * c2, o1 = (cxy.y & 0xffffu) * c2, oP = (cxy.y >> 16) * c2;
-                        tb[1] = ldg4(r0 + oM); tb[2] = ldg4(r0 + o0); tb[3] = ldg4(r0 + o1); tb[4] = ldg4(r0 + oP);      // aM0 a00 a10 aP0
-                        tb[5] = ldg4(r1 + oM); tb[6] = ldg4(r1 + o0); tb[7] = ldg4(r1 + o1); tb[8] = ldg4(r1 + oP);      // aM1 a01 a11 aP1
-                        tb[9] = ldg4(rm + o0); tb[10] = ldg4(rm + o1); tb[11] = ldg4(rp + o0); tb[12] = ldg4(rp + o1);   // a0m a1m a0p a1p
+                        tb[1] = ldt(r0 + oM); tb[2] = ldt(r0 + o0); tb[3] = ldt(r0 + o1); tb[4] = ldt(r0 + oP);      // aM0 a00 a10 aP0
+                        tb[5] = ldt(r1 + oM); tb[6] = ldt(r1 + o0); tb[7] = ldt(r1 + o1); tb[8] = ldt(r1 + oP);      // aM1 a01 a11 aP1
+                        tb[9] = ldt(rm + o0); tb[10] = ldt(rm + o1); tb[11] = ldt(rp + o0); tb[12] = ldt(rp + o1);   // a0m a1m a0p a1p
                     }
                 }
                 if (jc == 0) { m11 = m12 = m22 = q1 = q2 = 0.f; }
@@ -428,6 +468,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         bool new_span = true;
         uint32_t accH = 0, accL = 0;
 
+        const uint64_t pol_basis = prm.l2_hints >= 1 ? l2_policy_evict_first() : l2_policy_evict_normal();     // the basis is read exactly once
         auto issue_tma = [&](int t) {                        // basis tile t -> stage t % NST (elected thread)
             const int st = t % NST;
             const TileCoord tc = tile_coord(prm, t_begin + t);
@@ -435,11 +476,11 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
             unsigned char* dst = base + SM::off_A + st * STAGE_A;
             if (grid2d) {
 #pragma unroll
-                for (int blk = 0; blk < KBLK; ++blk) tma_load_3d(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[st]);
+                for (int blk = 0; blk < KBLK; ++blk) tma_load_3d_hint(dst + blk * 8192, &tmapB, blk * 32, tc.tx0, tc.b * prm.grid_h + tc.ty0, &fullB[st], pol_basis);
             } else {
                 const int row = tc.b * N + tc.n0;
 #pragma unroll
-                for (int blk = 0; blk < KBLK; ++blk) tma_load_2d(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[st]);
+                for (int blk = 0; blk < KBLK; ++blk) tma_load_2d_hint(dst + blk * 8192, &tmapB, blk * 32, row, &fullB[st], pol_basis);
             }
         };
         auto flush = [&](int sp) {

@@ -36,7 +36,8 @@ int lm_build_tc7_launch(int mode, int nch, int kblk, const CUtensorMap& tmB, con
                         cudaStream_t st);
 bool lm_build_tc7_supported(int mode, int nch, int kblk);
 
-static banet_tuning_t g_tuning = {0, 0, 4};
+constexpr int kTc6DefaultBandRows = 1, kTc6DefaultL2Hints = 0, kTc6DefaultTapPrefetch = 0;
+static banet_tuning_t g_tuning = {0, 0, 4, 0, 0, 0};
 void set_tuning(const banet_tuning_t& t) { g_tuning = t; }
 const banet_tuning_t& tuning() { return g_tuning; }
 
@@ -99,7 +100,7 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
     prm.tiles_per_pair = plan.tiles_per_pair; prm.total_tiles = plan.total_tiles;
     prm.grid_w = lv->grid_w; prm.grid_h = lv->grid_h;
     prm.tiles_x = lv->grid_w > 0 ? (lv->grid_w + 7) / 8 : 0; prm.tiles_y = lv->grid_h > 0 ? (lv->grid_h + 7) / 8 : 0;
-    prm.band_rows = 1; prm.kq_i = 0; prm.kq_j = 0;
+    prm.band_rows = 1; prm.l2_hints = 0; prm.tap_prefetch = 0; prm.kq_i = 0; prm.kq_j = 0;
     prm.hdd_transposed = 1;
     prm.force_direct = g_tuning.tc7_force_direct;
     prm.trace = nullptr;
@@ -116,6 +117,12 @@ int lm_build_tc(const banet_level_t* lv, const BuildPlan& plan, int mode, const 
         if (rc) return rc;
         rc = lm_build_tc7_launch(mode, nch, kblk, tm, tmF, tmC, prm, plan.grid, st);
     } else {
+        // dense grid: band walk + L2 policy (defaults picked from the B200 measurements in profiles/r02c_*)
+        int band = g_tuning.tc6_band_rows > 0 ? g_tuning.tc6_band_rows : kTc6DefaultBandRows;
+        if (band > prm.tiles_y) band = prm.tiles_y;
+        prm.band_rows = lv->grid_w > 0 && band > 1 ? band : 1;
+        prm.l2_hints = g_tuning.tc6_l2_hints > 0 ? g_tuning.tc6_l2_hints - 1 : kTc6DefaultL2Hints;
+        prm.tap_prefetch = g_tuning.tc6_tap_prefetch > 0 ? g_tuning.tc6_tap_prefetch - 1 : kTc6DefaultTapPrefetch;
         rc = lm_build_tc6_launch(mode, fly, nch, kblk, tm, prm, plan.grid, st);
     }
     if (rc) return rc;

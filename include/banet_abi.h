@@ -47,6 +47,9 @@ typedef struct banet_tuning {
     int tc_generation;      /* 0 or 6: generation 6 (ld.global taps; the default: fastest measured); 7: TMA-staged F2 windows where they apply (F2-only layout + dense grid) */
     int tc7_force_direct;   /* 1: generation 7 takes its per-tile global-tap fallback for every tile (tests the fallback) */
     int tc7_band_rows;      /* generation 7 walks the 8x8 tiles of a pair in bands of this many tile rows (L2 reuse of the window halos); default 4 */
+    int tc6_band_rows;      /* generation 6, dense grid: same walk (tap rows shared by vertically adjacent tiles are re-read from L2, not HBM); 0 = default, 1 = row-major */
+    int tc6_l2_hints;       /* generation 6: 0 = default; 1 = no L2 policy; 2 = read-once streams (basis TMA, conv1) evict-first; 3 = 2 + taps evict-last */
+    int tc6_tap_prefetch;   /* generation 6: 0 = default; 1 = off; 2 = geometry warps prefetch the tap footprint into L2 ahead of the gather; 3 = 2 with the lower tap row from every pixel */
 } banet_tuning_t;
 int banet_set_tuning(const banet_tuning_t* t);   /* NULL restores the defaults */
 int banet_get_tuning(banet_tuning_t* t);
