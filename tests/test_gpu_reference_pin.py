@@ -57,3 +57,41 @@ def test_reference_op_reproduces_committed_golden():
     dJ, dG, dd = ref.equation_construction_grad(J, G, d, lg, rg)
     for got, key in ((A, "out_AtA"), (b, "out_Atb"), (dJ, "out_dJ"), (dG, "out_dG"), (dd, "out_dd")):
         assert rel_fro(got, z[key]) < 1e-5, key
+
+
+def test_reference_op_timed_beside_the_b200_kernels():
+    """The reference's own CUDA op (cuBLAS batched SGEMM chain + its serial column reduction, utils.cu:331-414 / :613-690) and the B200
+    kernels behind the same op boundary, timed on the same GPU at the reference's own scale (nb=2, 4096 sampled points, legacy/seq_example.py:12)
+    and at a 160x120 level.  Also the fused layer-level build (never materialises J, G, d) at the same shape.  Report only (written to
+    gpurun_out/ref_op_timing.json when that directory exists); the single assertion is that the replacement is not slower."""
+    import json, time
+    from banet_b200 import ops, synth
+    ref = _ref()
+    report = []
+    for nb, gh, gw in ((2, 64, 64), (4, 120, 160)):
+        N, C, K = gh * gw, 128, 128; P = K + 6
+        g = torch.Generator().manual_seed(7)
+        J = torch.randn(nb, N, 2, P, generator=g).cuda(); G = torch.randn(nb, N, C, 2, generator=g).cuda(); d = torch.randn(nb, N, C, 1, generator=g).cuda()
+        lg = torch.randn(nb, P, P, generator=g).cuda(); rg = torch.randn(nb, P, 1, generator=g).cuda()
+
+        def wall(fn, reps=5):           # the reference harness synchronises the device itself: wall clock around synchronous calls
+            fn(); torch.cuda.synchronize(); ts = []
+            for _ in range(reps):
+                t0 = time.perf_counter(); fn(); torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+            return sorted(ts)[len(ts) // 2] * 1e3
+        row = {"nb": nb, "N": N, "C": C, "P": P,
+               "reference_fwd_ms": wall(lambda: ref.equation_construction(J, G, d)),
+               "reference_bwd_ms": wall(lambda: ref.equation_construction_grad(J, G, d, lg, rg)),
+               "b200_eqc_fwd_ms": wall(lambda: ops.equation_construction(J, G, d)),
+               "b200_eqc_bwd_ms": wall(lambda: ops.equation_construction_grad(J, G, d, lg, rg))}
+        del J, G, d
+        sc = synth.make_scene(nb=nb, H=gh, W=gw, C=C, K=K, level_ids=(3,), seed=11, device="cuda", dtype=torch.float32)
+        lv = sc.levels[0]; L = ops.Level(lv.conv1, lv.conv2, lv.intr, lv.p, lv.D, lv.B, grid=lv.grid)
+        row["b200_fused_build_fp32_ms"] = wall(lambda: ops.lm_build(L, sc.R0, sc.T0, sc.W0, precision=0))
+        row["b200_fused_build_auto_ms"] = wall(lambda: ops.lm_build(L, sc.R0, sc.T0, sc.W0, precision=-1))
+        report.append(row)
+        print(row)
+        assert row["b200_eqc_fwd_ms"] < row["reference_fwd_ms"] and row["b200_eqc_bwd_ms"] < row["reference_bwd_ms"]
+    out = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(report, open(os.path.join(out, "ref_op_timing.json"), "w"), indent=1)
