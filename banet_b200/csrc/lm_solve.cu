@@ -22,18 +22,22 @@ lm_lambda_kernel(const float* __restrict__ rbar_sum, int N, int C, const float* 
     extern __shared__ float sm[];
     float* bufA = sm;               // up to 4C
     float* bufB = sm + 4 * C;       // up to 4C
-    __shared__ float s_norm2;
+    __shared__ float s_norm2, s_wpart[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float invN = 1.0f / (float)N;
-    if (tid == 0) s_norm2 = 0.f;
-    __syncthreads();
     float part = 0.f;
     for (int c = tid; c < C; c += blockDim.x) {
         const float r = rbar_sum[(size_t)b * C + c] * invN;           // tf.reduce_mean over N (bundlenet.py:243)
         bufA[c] = r; part += r * r;
     }
     part = warp_sum(part);
-    if ((tid & 31) == 0) atomicAdd(&s_norm2, part);
+    if ((tid & 31) == 0) s_wpart[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {                                                     // fixed order: bit-reproducible (a float atomic here was not)
+        float t = 0.f;
+        for (int wq = 0; wq < (int)((blockDim.x + 31) >> 5); ++wq) t += s_wpart[wq];
+        s_norm2 = t;
+    }
     __syncthreads();
     const int dims[6] = {C, 2 * C, 4 * C, 2 * C, C, 1};
     const float* wp = mlp;

@@ -31,10 +31,11 @@ __device__ __forceinline__ float selu_s(float x) {
 }
 __host__ __device__ __forceinline__ int tri3(int i, int k) { return i * (i + 1) / 2 + k; }
 
-// one dense layer: out[j] = act(bias[j] + sum_i in[i] W[i][j]);  W row-major [cin][cout].  Tasks = (32-output block) x (input slice); partial
-// sums meet in `acc` (shared, zeroed by the caller) through shared-memory atomics; one barrier later the activation is applied.
+// one dense layer: out[j] = act(bias[j] + sum_i in[i] W[i][j]);  W row-major [cin][cout].  Tasks = (32-output block) x (input slice); every task
+// stores its partial sums into its own row of `part` ([slices][cout], at most max(1024, cout) floats) and the activation pass adds the slices in
+// a fixed order: bit-reproducible (shared-memory float atomics were not: lambda, and with it the whole step, moved in the last ulp run to run).
 __device__ __forceinline__ void dense_layer(const float* __restrict__ in, const float* __restrict__ Wm, const float* __restrict__ bias,
-                                            int cin, int cout, bool last, float* __restrict__ acc, float* __restrict__ out, int tid)
+                                            int cin, int cout, bool last, float* __restrict__ part, float* __restrict__ out, int tid)
 {
     const int lane = tid & 31, warp = tid >> 5;
     const int jblocks = (cout + 31) / 32;
@@ -64,12 +65,14 @@ __device__ __forceinline__ void dense_layer(const float* __restrict__ in, const 
                 a0 = fmaf(in[i + 4], w4, a0); a1 = fmaf(in[i + 5], w5, a1); a2 = fmaf(in[i + 6], w6, a2); a3 = fmaf(in[i + 7], w7, a3);
             }
             for (; i < i1; ++i) a0 = fmaf(in[i], __ldg(Wm + (size_t)i * cout + j), a0);
-            atomicAdd(&acc[j], (a0 + a1) + (a2 + a3));
+            part[sl * cout + j] = (a0 + a1) + (a2 + a3);
         }
     }
     __syncthreads();
     for (int j = tid; j < cout; j += STEP_THREADS) {
-        const float z = acc[j] + __ldg(bias + j);
+        float z = part[j];
+        for (int sl = 1; sl < slices; ++sl) z += part[sl * cout + j];
+        z += __ldg(bias + j);
         out[j] = last ? tanhf(z) : selu_s(z);
     }
     __syncthreads();
@@ -94,11 +97,11 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
     S* xs = A + nA;                                                  // [P] solution
     S* dinv = xs + P;                                                // [P] reciprocals of the Cholesky diagonal
     S* dots = dinv + P;                                              // [STEP_NB]
-    float* mbuf = reinterpret_cast<float*>(dots + STEP_NB);          // MLP buffers: 3 x 4C floats
+    float* mbuf = reinterpret_cast<float*>(dots + STEP_NB);          // MLP buffers: 2 x 4C floats + max(4C, 1024) floats of slice partials
     __shared__ int s_flag;
-    __shared__ float s_norm2, s_lam;
+    __shared__ float s_wpart[STEP_WARPS], s_lam;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, K = P - 6;
-    if (tid == 0) { s_flag = 0; s_norm2 = 0.f; }
+    if (tid == 0) s_flag = 0;
     __syncthreads();
 
     // ---- 1. lambda -------------------------------------------------------------------------------------------------------------------
@@ -109,9 +112,8 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         const float invN = 1.0f / (mode.rbar_per_valid ? nvalid[b] : (float)N);
         float part = 0.f;
         for (int c = tid; c < C; c += STEP_THREADS) { const float r = rbar_sum[(size_t)b * C + c] * invN; bufA[c] = r; part += r * r; }
-        for (int c = tid; c < 4 * C; c += STEP_THREADS) acc[c] = 0.f;
         part = warp_sum(part);
-        if (lane == 0 && part != 0.f) atomicAdd(&s_norm2, part);
+        if (lane == 0) s_wpart[warp] = part;
         __syncthreads();
         const int dims[6] = {C, 2 * C, 4 * C, 2 * C, C, 1};
         const float* wp = mlp;
@@ -119,13 +121,16 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
         for (int l = 0; l < (mlp ? 5 : 0); ++l) {
             const int cin = dims[l], cout = dims[l + 1];
             dense_layer(in, wp, wp + (size_t)cin * cout, cin, cout, l == 4, acc, out, tid);
-            for (int c = tid; c < cout; c += STEP_THREADS) acc[c] = 0.f;       // ready for the next layer (visible after its first barrier)
             wp += (size_t)cin * cout + cout;
             float* tmp = in; in = out; out = tmp;
             __syncthreads();
         }
         // bundlenet.py:249,253: base * ||rbar||^(2 + h); legacy/ba.py:280: ||rbar||^(1 + h); no MLP (legacy/ba.py:190): h = 0
-        if (tid == 0) { s_lam = base * powf(sqrtf(s_norm2), mode.lambda_exp0 + (mlp ? in[0] : 0.f)); lambda_out[b] = s_lam; }
+        if (tid == 0) {
+            float norm2 = 0.f;
+            for (int wq = 0; wq < STEP_WARPS; ++wq) norm2 += s_wpart[wq];               // fixed order
+            s_lam = base * powf(sqrtf(norm2), mode.lambda_exp0 + (mlp ? in[0] : 0.f)); lambda_out[b] = s_lam;
+        }
         __syncthreads();
         lam = s_lam;
     } else {
@@ -313,7 +318,7 @@ lm_step_kernel(const float* __restrict__ H, const float* __restrict__ g, const f
 size_t lm_step_smem(int P, int C, bool use_double, bool full)
 {
     const size_t nA = (full ? (size_t)(P + 1) * ((P + 1) | 1) : (size_t)(P + 1) * (P + 2) / 2) + 2 * (size_t)P + STEP_NB;
-    return nA * (use_double ? sizeof(double) : sizeof(float)) + (size_t)12 * C * sizeof(float);
+    return nA * (use_double ? sizeof(double) : sizeof(float)) + ((size_t)8 * C + (4 * C > 1024 ? 4 * C : 1024)) * sizeof(float);
 }
 
 bool lm_step_supported(int P, int C) { return lm_step_smem(P, C, false, false) <= 220 * 1024; }
