@@ -258,19 +258,14 @@ def lm_step(H: Tensor, g: Tensor, rbar_sum: Optional[Tensor], N: int, mlp_packed
     return Ro, To, Wo, delta, lout, status
 
 
-def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
-           mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: Optional[float] = None,
-           lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,
-           vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_AUTO, workspace: Optional[Tensor] = None):
-    """Whole coarse-to-fine solve on the device (banet_lm_run).  Returns new (R,T,W,status); inputs are not modified."""
+def _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last, vmatrix_batch_scramble, precision):
+    """Argument block of banet_lm_run shared by lm_run and LMRunGraph: level structs, lambda-MLP pointers, options, workspace size."""
     lib = load()
     structs, keep = [], []
     for lv in levels:
         s, k = lv.as_struct(); structs.append(s); keep.append(k)
     arr = (BanetLevel * len(structs))(*structs)
     nb, K = structs[0].nb, structs[0].K
-    R = _chk(R, "R", (nb, 3, 3)).clone(); T = _chk(T, "T", (nb, 3, 1)).clone()
-    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1)).clone()
     if undamped_last is None:
         undamped_last = K > 0
     if l2_regularizer_base is None:              # BundleIteration scales lambda by 1000 (bundlenet.py:252-253, 393); CameraIteration ignores the base (:165-173)
@@ -288,12 +283,67 @@ def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, 
     nbytes = lib.banet_lm_run_workspace_bytes(arr, len(structs), precision)
     if nbytes == 0:
         check(-4, "banet_lm_run_workspace_bytes")
+    return arr, len(structs), nb, K, (mlp_ptrs if have else None), float(l2_regularizer_base), opts, int(nbytes), keep
+
+
+def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Optional[Tensor],
+           mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: Optional[float] = None,
+           lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: Optional[bool] = None,
+           vmatrix_batch_scramble: bool = False, precision: int = _lib.PREC_AUTO, workspace: Optional[Tensor] = None):
+    """Whole coarse-to-fine solve on the device (banet_lm_run).  Returns new (R,T,W,status); inputs are not modified."""
+    lib = load()
+    arr, nlev, nb, K, mlp_ptrs, base, opts, nbytes, _keep = _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last,
+                                                                         vmatrix_batch_scramble, precision)
+    R = _chk(R, "R", (nb, 3, 3)).clone(); T = _chk(T, "T", (nb, 3, 1)).clone()
+    Wt = None if K == 0 else _chk(W, "W", (nb, K, 1)).clone()
     ws = workspace if workspace is not None and workspace.numel() >= nbytes else _ws(nbytes, R.device)
     status = torch.empty(nb, device=R.device, dtype=torch.int32)
-    check(lib.banet_lm_run(arr, len(structs), int(iters_per_level), mlp_ptrs if have else None, float(l2_regularizer_base),
-                           float(lambda_fixed), C.byref(opts), precision, R.data_ptr(), T.data_ptr(), _ptr(Wt),
-                           status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_run")
+    check(lib.banet_lm_run(arr, nlev, int(iters_per_level), mlp_ptrs, base, float(lambda_fixed), C.byref(opts), precision,
+                           R.data_ptr(), T.data_ptr(), _ptr(Wt), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_run")
     return R, T, Wt, status
+
+
+class LMRunGraph:
+    """`banet_lm_run` captured ONCE into a CUDA graph and replayed: the library call allocates nothing and never synchronises, so the whole
+    coarse-to-fine loop (3 launches per LM iteration) is capturable as it is.  For small or sparse problems (the reference's 4096-point
+    tracking mode, coarse levels), where launch gaps are a visible share of a solve.  Results are bit-identical to
+    `lm_run`.  The level tensors, lambda-MLP weights and the workspace are baked into the graph by address: keep them alive and refill them in
+    place between solves; `solve` copies the start iterate into the graph's static buffers and returns clones of the result."""
+
+    def __init__(self, levels: Sequence[Level], iters_per_level: int, mlp_packed: Optional[Sequence[Optional[Tensor]]] = None,
+                 l2_regularizer_base: Optional[float] = None, lambda_fixed: float = -1.0, damping_eps: float = 1e-5,
+                 undamped_last: Optional[bool] = None, precision: int = _lib.PREC_AUTO):
+        self._lib = load()
+        (self._arr, self._nlev, self.nb, self.K, self._mlp_ptrs, self._base, self._opts, nbytes, self._keep) = _prepare_run(
+            levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last, False, precision)
+        self._iters, self._lambda_fixed, self._prec = int(iters_per_level), float(lambda_fixed), int(precision)
+        dev = levels[0].conv1.device
+        self.R = torch.zeros(self.nb, 3, 3, device=dev); self.T = torch.zeros(self.nb, 3, 1, device=dev)
+        self.W = None if self.K == 0 else torch.zeros(self.nb, self.K, 1, device=dev)
+        self.status = torch.zeros(self.nb, device=dev, dtype=torch.int32)
+        self._ws = _ws(nbytes, dev)
+        self.R.copy_(torch.eye(3, device=dev).expand(self.nb, 3, 3))
+        side = torch.cuda.Stream(device=dev)                       # eager warm-up off the default stream (sets the kernels' attributes), then capture
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            self._launch()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._launch()
+
+    def _launch(self):
+        check(self._lib.banet_lm_run(self._arr, self._nlev, self._iters, self._mlp_ptrs, self._base, self._lambda_fixed, C.byref(self._opts),
+                                     self._prec, self.R.data_ptr(), self.T.data_ptr(), _ptr(self.W), self.status.data_ptr(),
+                                     self._ws.data_ptr(), self._ws.numel(), _stream()), "banet_lm_run")
+
+    def solve(self, R: Tensor, T: Tensor, W: Optional[Tensor]):
+        """-> new (R, T, W, status) like `lm_run`."""
+        self.R.copy_(_chk(R, "R", (self.nb, 3, 3))); self.T.copy_(_chk(T, "T", (self.nb, 3, 1)))
+        if self.K:
+            self.W.copy_(_chk(W, "W", (self.nb, self.K, 1)))
+        self.graph.replay()
+        return self.R.clone(), self.T.clone(), None if self.W is None else self.W.clone(), self.status.clone()
 
 
 def lm_run_workspace_bytes(levels: Sequence[Level], precision: int = _lib.PREC_AUTO) -> int:

@@ -258,17 +258,20 @@ def run_cfg4(args):
         packed = [ops.pack_mlp([(torch.randn(dims[i], dims[i + 1], generator=g) * (2.0 / dims[i]) ** 0.5, torch.zeros(dims[i + 1])) for i in range(5)]).to(dev) for _ in LEVEL_IDS]
         ws = torch.empty(ops.lm_run_workspace_bytes(levels, _lib.PREC_AUTO), dtype=torch.uint8, device=dev)
         ms = _time_ms(lambda: ops.lm_run(levels, iters, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0, workspace=ws), max(3, args.steps))
+        graph = ops.LMRunGraph(levels, iters, mlp_packed=packed, l2_regularizer_base=1000.0)       # the same call captured once into a CUDA graph
+        ms_graph = _time_ms(lambda: graph.solve(sc.R0, sc.T0, sc.W0), max(3, args.steps))
         N_tot = sum(l.N for l in sc.levels)
         # sparse points: no texel reuse, every point reads its own 4 taps of the 3C map
         by = nb * iters * sum((4 * l.N * (2 * C + K + 4) if npts is None else 4 * l.N * (C + 12 * C + K + 4)) + 4 * ((6 + K) ** 2 + 6 + K + C) for l in sc.levels)
         out.append({"variant": variant, "points_per_pair_sum_levels": N_tot, "ms_per_solve": ms, "pair_iters_per_s": nb * len(levels) * iters / (ms * 1e-3),
                     "algorithmic_gbs": by / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": by / (ms * 1e-3) / 1e9 / peak,
-                    "launches_per_solve": 1 + len(levels) * iters * 3})
-        del sc, levels
+                    "launches_per_solve": 1 + len(levels) * iters * 3, "ms_per_solve_cuda_graph": ms_graph,
+                    "pair_iters_per_s_cuda_graph": nb * len(levels) * iters / (ms_graph * 1e-3)})
+        del sc, levels, graph
         torch.cuda.empty_cache()
     print(json.dumps({"metric": METRIC, "unit": UNIT, "value": out[0]["pair_iters_per_s"], "n_gpus": 1, "higher_is_better": True, "data": "synthetic",
-                      "config": {"workload": "cfg4: keyframe + 4 frames as nb=4 pairs, 640x480 4-level pyramid, K=128, 10 LM iters/level; dense (F2-only layout, "
-                                             "generation-7 kernel) and sparse N=4096 random sub-pixel points per level ([F2|gx|gy] layout, ragged tiles)", "precision": "auto"},
+                      "config": {"workload": "cfg4: keyframe + 4 frames as nb=4 pairs, 640x480 4-level pyramid, K=128, 10 LM iters/level; dense (F2-only layout) "
+                                             "and sparse N=4096 random sub-pixel points per level ([F2|gx|gy] layout, ragged tiles)", "precision": "auto"},
                       "variants": out, "roofline": {"bound": "hbm (dense) / launch+latency (sparse)", "peak": peak, "peak_kind": peak_kind, "unit": "GB/s"}}))
 
 

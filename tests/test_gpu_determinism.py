@@ -67,3 +67,18 @@ def test_builds_and_steps_are_bit_reproducible(scene, monkeypatch, layout):
             assert torch.equal(a, b), (layout, li, "lm_step")
         n_pts = lv.conv1.shape[1]
         assert torch.equal(ops.lm_lambda(rbar, n_pts, packed[li], 1000.0), ops.lm_lambda(rbar, n_pts, packed[li], 1000.0))
+
+
+def test_captured_graph_replays_the_eager_solve_bit_for_bit(scene):
+    """ops.LMRunGraph: banet_lm_run captured once into a CUDA graph (nothing in the call allocates or synchronises)."""
+    from banet_b200 import ops, _lib
+    sc, levels, packed = scene
+    eager = ops.lm_run(levels, 3, sc.R0, sc.T0, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0)
+    gr = ops.LMRunGraph(levels, 3, mlp_packed=packed, l2_regularizer_base=1000.0)
+    for _ in range(2):                                    # replays do not depend on what the previous replay left in the static buffers
+        out = gr.solve(sc.R0, sc.T0, sc.W0)
+        for a, b in zip(eager, out):
+            assert torch.equal(a, b)
+    R2 = sc.R0.clone(); T2 = sc.T0 * 0.5
+    for a, b in zip(ops.lm_run(levels, 3, R2, T2, sc.W0, mlp_packed=packed, l2_regularizer_base=1000.0), gr.solve(R2, T2, sc.W0)):
+        assert torch.equal(a, b)
