@@ -304,6 +304,72 @@ extern "C" int banet_lm_run(const banet_level_t* levels, int nlevels, int iters_
     return BANET_OK;
 }
 
+// ---- joint keyframe window (an extension, the reference is 2-view): nb = nf frame pairs sharing one W -------------
+extern "C" size_t banet_lm_window_run_workspace_bytes(const banet_level_t* levels, int nlevels, int precision)
+{
+    if (!levels || nlevels <= 0 || levels[0].K <= 0) return 0;
+    RunCarve c;
+    if (carve(levels, nlevels, precision, &c) != BANET_OK) return 0;
+    int maxC = 0;
+    for (int l = 0; l < nlevels; ++l) if (levels[l].C > maxC) maxC = levels[l].C;
+    return c.total + align_up(lm_window_step_workspace_floats(levels[0].nb, levels[0].K, maxC) * sizeof(float), 256);
+}
+
+extern "C" int banet_lm_window_run(const banet_level_t* levels, int nlevels, int iters_per_level,
+                                   const float* const* mlp_weights, float l2_regularizer_base, float lambda_fixed,
+                                   const banet_solve_opts_t* opts, int precision,
+                                   float* R, float* T, float* W, int32_t* status, void* ws, size_t ws_bytes, banet_stream_t stream)
+{
+    BANET_REQUIRE(levels && nlevels > 0 && iters_per_level > 0 && opts && R && T && W && status, BANET_ERR_BAD_ARG, "lm_window_run: bad argument");
+    const int nf = levels[0].nb, K = levels[0].K;
+    BANET_REQUIRE(K > 0 && !opts->vmatrix_batch_scramble, BANET_ERR_BAD_ARG, "lm_window_run: needs a depth basis (K > 0) and vmatrix_batch_scramble = 0");
+    int maxC = 0;
+    for (int l = 0; l < nlevels; ++l) {
+        int rc = check_level(&levels[l], "lm_window_run");
+        if (rc) return rc;
+        BANET_REQUIRE(levels[l].nb == nf && levels[l].K == K, BANET_ERR_BAD_ARG, "lm_window_run: nb/K must agree across levels");
+        BANET_REQUIRE((mlp_weights && mlp_weights[l]) || lambda_fixed >= 0.f, BANET_ERR_BAD_ARG,
+                      "lm_window_run: level %d has no lambda-MLP weights and lambda_fixed < 0", l);
+        BANET_REQUIRE(lm_window_supported(nf, K, levels[l].C), BANET_ERR_UNSUPPORTED, "lm_window_run: 6*%d+%d unknowns do not fit the solve kernel", nf, K);
+        if (levels[l].C > maxC) maxC = levels[l].C;
+    }
+    RunCarve c;
+    int rc = carve(levels, nlevels, precision, &c);
+    if (rc) return rc;
+    const size_t need = c.total + align_up(lm_window_step_workspace_floats(nf, K, maxC) * sizeof(float), 256);
+    BANET_REQUIRE(ws && ws_bytes >= need, BANET_ERR_WORKSPACE, "lm_window_run: workspace %zu < %zu bytes", ws_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* base = reinterpret_cast<char*>(ws);
+    float* H = reinterpret_cast<float*>(base + c.H);
+    float* g = reinterpret_cast<float*>(base + c.g);
+    float* rbar = reinterpret_cast<float*>(base + c.rbar);
+    float* nvalid = reinterpret_cast<float*>(base + c.nvalid);
+    float* lam = reinterpret_cast<float*>(base + c.lambda);
+    float* wsw = reinterpret_cast<float*>(base + c.total);
+    zero_status_kernel<<<(nf + 255) / 256, 256, 0, st>>>(status, nf);
+    rc = lm_window_broadcast_w(W, nf, K, st);                      // frame 0's W is the window's W
+    if (rc) return rc;
+    for (int l = 0; l < nlevels; ++l) {
+        const banet_level_t* lv = &levels[l];
+        BuildPlan plan;
+        const int res = resolve_precision(lv, precision);
+        if (res < 0) return res;
+        rc = plan_for(lv, res, &plan);
+        if (rc) return rc;
+        const bool use_mlp = mlp_weights && mlp_weights[l] && lambda_fixed < 0.f;
+        if (!use_mlp) fill_kernel<<<1, 32, 0, st>>>(lam, 1, lambda_fixed);
+        for (int it = 0; it < iters_per_level; ++it) {
+            rc = build_dispatch(lv, res, plan, R, T, W, H, g, rbar, nvalid, base + c.build, st);
+            if (rc) return rc;
+            rc = lm_window_step(H, g, rbar, nf, lv->N, lv->C, K, use_mlp ? mlp_weights[l] : nullptr, l2_regularizer_base, use_mlp ? nullptr : lam,
+                                *opts, R, T, W, wsw, nullptr, status, st);
+            if (rc) return rc;
+        }
+    }
+    BANET_CUDA_LAUNCH_CHECK("lm_window_run");
+    return BANET_OK;
+}
+
 extern "C" size_t banet_lm_track_legacy_workspace_bytes(const banet_level_t* levels, int nlevels)
 {
     if (!levels || nlevels <= 0) return 0;

@@ -64,6 +64,16 @@ int lm_step(const float* H, const float* g, const float* rbar_sum, int nb, int N
             const StepMode& mode, const float* nvalid, const banet_solve_opts_t& opts, const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
             float* delta, float* lambda_out, int32_t* status, int status_accumulate, cudaStream_t st);
 
+int launch_pose_update(const float* delta, int nb, int P, const float* R, const float* T, float* R_out, float* T_out, cudaStream_t st);
+
+// joint step of a keyframe window: nf pairs sharing one W (lm_window.cu); ws: lm_window_step_workspace_floats floats
+bool lm_window_supported(int nf, int K, int C);
+size_t lm_window_step_workspace_floats(int nf, int K, int C);
+int lm_window_broadcast_w(float* W, int nf, int K, cudaStream_t st);
+int lm_window_step(const float* H, const float* g, const float* rbar_sum, int nf, int N, int C, int K, const float* mlp, float base,
+                   const float* lambda_in, const banet_solve_opts_t& opts, float* R, float* T, float* W, float* ws, float* lambda_out,
+                   int32_t* status, cudaStream_t st);
+
 // legacy pose-only tracker loop with device-side accept / reject and early termination (lm_legacy.cu)
 size_t lm_track_legacy_workspace_bytes(const banet_level_t* levels, int nlevels);
 int lm_track_legacy(const banet_level_t* levels, int nlevels, const int* level_iters, const float* const* mlp_weights, const banet_legacy_opts_t& o,

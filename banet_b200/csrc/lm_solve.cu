@@ -231,6 +231,13 @@ __global__ void pose_update_kernel(const float* __restrict__ delta, int nb, int 
     }
 }
 
+int launch_pose_update(const float* delta, int nb, int P, const float* R, const float* T, float* R_out, float* T_out, cudaStream_t st)
+{
+    pose_update_kernel<<<(nb + 127) / 128, 128, 0, st>>>(delta, nb, P, 0, R, T, R_out, T_out);     // every thread reads its pair before it writes: in place is fine
+    BANET_CUDA_LAUNCH_CHECK("pose_update_kernel launch");
+    return BANET_OK;
+}
+
 int lm_solve_update(const float* H, const float* g, const float* lambda, int nb, int K, const banet_solve_opts_t& opts,
                     const float* R, const float* T, const float* W, float* R_out, float* T_out, float* W_out,
                     float* delta, int32_t* status, int status_accumulate, cudaStream_t st)

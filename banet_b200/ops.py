@@ -258,7 +258,7 @@ def lm_step(H: Tensor, g: Tensor, rbar_sum: Optional[Tensor], N: int, mlp_packed
     return Ro, To, Wo, delta, lout, status
 
 
-def _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last, vmatrix_batch_scramble, precision):
+def _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last, vmatrix_batch_scramble, precision, window: bool = False):
     """Argument block of banet_lm_run shared by lm_run and LMRunGraph: level structs, lambda-MLP pointers, options, workspace size."""
     lib = load()
     structs, keep = [], []
@@ -280,9 +280,9 @@ def _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_
                 raise _lib.BanetError("mlp_packed size mismatch")
         mlp_ptrs[i] = None if m is None else m.data_ptr()
     opts = BanetSolveOpts(float(damping_eps), int(undamped_last), int(vmatrix_batch_scramble))
-    nbytes = lib.banet_lm_run_workspace_bytes(arr, len(structs), precision)
+    nbytes = (lib.banet_lm_window_run_workspace_bytes if window else lib.banet_lm_run_workspace_bytes)(arr, len(structs), precision)
     if nbytes == 0:
-        check(-4, "banet_lm_run_workspace_bytes")
+        check(-4, "banet_lm_window_run_workspace_bytes" if window else "banet_lm_run_workspace_bytes")
     return arr, len(structs), nb, K, (mlp_ptrs if have else None), float(l2_regularizer_base), opts, int(nbytes), keep
 
 
@@ -301,6 +301,26 @@ def lm_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, 
     check(lib.banet_lm_run(arr, nlev, int(iters_per_level), mlp_ptrs, base, float(lambda_fixed), C.byref(opts), precision,
                            R.data_ptr(), T.data_ptr(), _ptr(Wt), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "banet_lm_run")
     return R, T, Wt, status
+
+
+def lm_window_run(levels: Sequence[Level], iters_per_level: int, R: Tensor, T: Tensor, W: Tensor,
+                  mlp_packed: Optional[Sequence[Optional[Tensor]]] = None, l2_regularizer_base: Optional[float] = None,
+                  lambda_fixed: float = -1.0, damping_eps: float = 1e-5, undamped_last: bool = True,
+                  precision: int = _lib.PREC_AUTO, workspace: Optional[Tensor] = None):
+    """Joint coarse-to-fine solve of a keyframe window (banet_lm_window_run; an extension): the nf pairs of every
+    level are (keyframe -> frame f) and share ONE depth-coefficient vector.  R [nf,3,3], T [nf,3,1] per frame, W [K,1] (or [1,K,1]) shared.
+    Returns new (R, T, W [K,1], status [nf])."""
+    lib = load()
+    arr, nlev, nf, K, mlp_ptrs, base, opts, nbytes, _keep = _prepare_run(levels, mlp_packed, l2_regularizer_base, damping_eps, undamped_last,
+                                                                         False, precision, window=True)
+    R = _chk(R, "R", (nf, 3, 3)).clone(); T = _chk(T, "T", (nf, 3, 1)).clone()
+    Wt = _chk(W.reshape(1, K, 1), "W", (1, K, 1)).repeat(nf, 1, 1).contiguous()
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else _ws(nbytes, R.device)
+    status = torch.empty(nf, device=R.device, dtype=torch.int32)
+    check(lib.banet_lm_window_run(arr, nlev, int(iters_per_level), mlp_ptrs, base, float(lambda_fixed), C.byref(opts), precision,
+                                  R.data_ptr(), T.data_ptr(), Wt.data_ptr(), status.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+          "banet_lm_window_run")
+    return R, T, Wt[0].clone(), status
 
 
 class LMRunGraph:

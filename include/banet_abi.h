@@ -214,6 +214,23 @@ int    banet_lm_run(const banet_level_t* levels, int nlevels, int iters_per_leve
                     void* ws, size_t ws_bytes, banet_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * (3c) Joint keyframe window — an EXTENSION, not in the reference: its BA layer is 2-view (one pose and one W
+ *      per pair, bundlenet.py:193-278) and BA-Net's 5-frame case runs as 4 independent pairs (legacy/seq_example.py).  Here the nb = nf
+ *      pairs of every level are (keyframe -> frame f) and share the keyframe's depth D + B.W: 6 nf + K unknowns, block-arrow normal
+ *      matrix (per-pair pose blocks and pose-depth couplings from banet_lm_build, depth block and depth right-hand side summed over the
+ *      frames), lambda from the mean |residual| over all points of all frames through the same MLP (bundlenet.py:241-253), the
+ *      reference's damping (:264-266, last depth coefficient undamped), ONE solve, per-frame SE(3) update (:269-275), shared W update.
+ *      Same arguments as banet_lm_run.  conv1, p, D, B of a level hold the keyframe's tensors once per frame (the [nb,...] layout).
+ *      W [nf,K,1]: frame 0's row is the window's W on entry (it is broadcast), every row holds the shared result on exit.
+ *      status [nf]: the window's status (a skipped step skips every frame).  6 nf + K must fit the fused solve (<= ~220). */
+size_t banet_lm_window_run_workspace_bytes(const banet_level_t* levels, int nlevels, int precision);
+int    banet_lm_window_run(const banet_level_t* levels, int nlevels, int iters_per_level,
+                           const float* const* mlp_weights, float l2_regularizer_base, float lambda_fixed,
+                           const banet_solve_opts_t* opts, int precision,
+                           float* R, float* T, float* W, int32_t* status,
+                           void* ws, size_t ws_bytes, banet_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * (4) The legacy pose-only keyframe tracker loop: legacy/ba.py:83-145 (`Tracker.trackTF`) with CameraIteration (:147-214) or, with
  *     early termination, CameraIteration2 (:226-345: lambda-MLP step, residual re-evaluated at the updated pose, step kept only if it
  *     decreased) — accept / reject and the per-level termination test run on the device, per pair, without host synchronisation.

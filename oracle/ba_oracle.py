@@ -451,6 +451,62 @@ def lm_solve_structured(levels, iters_per_level: int, R, T, W=None, opts: IterOp
     return R, T, W
 
 
+# --------------------------------------------------------------------------- joint keyframe window (extension)
+def window_assemble(H: Tensor, g: Tensor) -> Tuple[Tensor, Tensor]:
+    """Per-pair normal equations of nf pairs that share one W -> the block-arrow system of the window: pose blocks and pose-depth
+    couplings per frame, depth block and depth right-hand side summed over the frames.  H [nf,P,P], g [nf,P,1] -> Hj [Pj,Pj], gj [Pj,1],
+    Pj = 6 nf + K."""
+    nf, P, _ = H.shape
+    K = P - 6
+    Pj = 6 * nf + K
+    Hj = torch.zeros(Pj, Pj, dtype=H.dtype); gj = torch.zeros(Pj, 1, dtype=H.dtype)
+    for f in range(nf):
+        s = slice(6 * f, 6 * f + 6)
+        Hj[s, s] = H[f, :6, :6]
+        Hj[s, 6 * nf:] = H[f, :6, 6:]
+        Hj[6 * nf:, s] = H[f, 6:, :6]
+        Hj[6 * nf:, 6 * nf:] += H[f, 6:, 6:]
+        gj[s] = g[f, :6]
+        gj[6 * nf:] += g[f, 6:]
+    return Hj, gj
+
+
+def window_iteration(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, W, mlp_params, opts: IterOptions = IterOptions(), chunk: int = 32768):
+    """One joint LM iteration of a keyframe window.  NOT in the reference (its BA layer is 2-view, bundlenet.py:193-278; SURVEY.md
+    section 8f-4 lists the window as an extension): the nf pairs (keyframe -> frame f) share the keyframe depth D + B.W, W [K,1].
+    Everything else follows BundleIteration: per-pair residuals / Jacobians (:206-261), lambda from the mean |residual| over all points
+    of all frames (:241-253), damping of every diagonal entry but the last depth coefficient (:264-266), one solve (:267), per-frame
+    SE(3) update (:269-275), shared W update (:276).  -> (R' [nf,3,3], T' [nf,3,1], W' [K,1])."""
+    nf = conv1.shape[0]
+    K = B.shape[-1]
+    Wrep = W.reshape(1, K, 1).expand(nf, K, 1)
+    H, g, rbar, _ = normal_equations_structured_chunked(conv1, conv2, fx, fy, ox, oy, p, D, B, R, T, Wrep, opts.guard_nonfinite, chunk)
+    Hj, gj = window_assemble(H, g)
+    avg = rbar.mean(dim=0, keepdim=True)                              # every frame has N points: mean over all nf * N
+    if opts.lambda_override is not None:
+        lam = opts.lambda_override.reshape(-1)[0].to(conv1.dtype)
+    else:
+        lam = torch.pow(torch.linalg.norm(avg, dim=-1, keepdim=True), 2.0 + lambda_mlp(avg, mlp_params)).reshape(())
+        if opts.l2_regularizer_base is not None:
+            lam = opts.l2_regularizer_base * lam
+    diag = torch.diagonal(Hj)
+    dvec = diag + opts.damping_eps
+    if opts.undamped_last:
+        dvec = torch.cat([dvec[:-1], torch.zeros(1, dtype=diag.dtype)])
+    sol = torch.linalg.solve(Hj + torch.diag(dvec * lam), gj)
+    pose = sol[:6 * nf].reshape(nf, 6, 1)
+    Rn, Tn = _update(pose, R, T, opts)
+    return Rn, Tn, W.reshape(K, 1) + sol[6 * nf:]
+
+
+def window_solve(levels, iters_per_level: int, R, T, W, opts: IterOptions = IterOptions(), chunk: int = 32768):
+    """Coarse-to-fine loop of `window_iteration` over `LevelInputs` (nb = nf pairs per level)."""
+    for lv in levels:
+        for _ in range(iters_per_level):
+            R, T, W = window_iteration(lv.conv1, lv.conv2, lv.fx, lv.fy, lv.ox, lv.oy, lv.p, lv.D, lv.B, R, T, W, lv.mlp, opts, chunk)
+    return R, T, W
+
+
 # --------------------------------------------------------------------------- schedulers
 @dataclass
 class ResizeGeometry:
