@@ -29,6 +29,53 @@ def chunk_ranges(nb: int, chunks: int) -> List[Tuple[int, int]]:
     return out
 
 
+
+class numa_local_to:
+    """Context manager: while it is active the calling thread runs on the CPUs of the NUMA node the given GPU hangs off, so that host buffers
+    allocated (and pinned) inside it are placed in the memory next to that GPU's PCIe root (first-touch placement).  With several GPUs per
+    host this keeps every rank's host->device traffic off the inter-socket link.  Restores the previous affinity on exit.  A no-op (with
+    `.info` saying why) when the topology cannot be read — it never fails the caller."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.info = {"node": None, "cpus": None, "note": "not applied"}
+        self._saved = None
+
+    def __enter__(self):
+        import os
+        try:
+            pr = torch.cuda.get_device_properties(self.device)
+            bdf = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+            if node < 0:
+                self.info["note"] = f"{bdf}: numa_node unknown (-1)"
+                return self
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+            self._saved = os.sched_getaffinity(0)
+            use = cpus & self._saved
+            if not use:
+                self.info["note"] = f"node {node}: none of its CPUs is in this process's affinity mask"
+                self._saved = None
+                return self
+            os.sched_setaffinity(0, use)
+            self.info = {"node": node, "cpus": len(use), "note": f"{bdf}: host buffers allocated on NUMA node {node}"}
+        except Exception as ex:                                    # sysfs not mounted, property missing, permission: stay as we are
+            self.info["note"] = f"topology unavailable ({type(ex).__name__})"
+            self._saved = None
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self._saved is not None:
+            try:
+                os.sched_setaffinity(0, self._saved)
+            except Exception:
+                pass
+        return False
+
 class HostSolver:
     """host_levels: one dict per level (coarse -> fine) with host tensors conv1 [nb,N,C], conv2 [nb,h,w,C] (features; gradients
     are derived on the device) or [nb,h,w,3C] (already [F2|gx|gy]) when derive_gradients=False, intr [nb,4], p [nb,3,N],

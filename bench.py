@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
+    ap.add_argument("--motion", default="default", choices=["default", "large"],
+                    help="planted relative motion of the synthetic pairs: default 1 deg / 2 cm (SURVEY.md section 8d), large 4 deg / 8 cm (less tap locality, fewer in-bounds points)")
     ap.add_argument("--e2e-boundary", default="resize", choices=["resize", "features", "concat"],
                     help="host buffers of the e2e leg: 'resize' = the reference's BundleResize boundary (bundlenet.py:332-399): the image batch's feature "
                          "pyramid, half-resolution basis / depth and intrinsics in; conv1, conv2, p, D, B derived on the device (ResizeHostSolver); "
@@ -343,8 +345,9 @@ def main():
         td.init_process_group("nccl", device_id=dev)
 
     C, K, nb, iters = args.channels, args.bases, args.nb, args.iters
+    motion = dict(rot_deg=4.0, trans_m=0.08, start_trans_noise_m=0.02) if args.motion == "large" else {}
     sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 2 + 1000 * rank,
-                          device=dev, dtype=torch.float32)
+                          device=dev, dtype=torch.float32, **motion)
     if args.layout == "f2":            # keep only the feature third of conv2 (the gradients are recomputed on the fly by the kernel)
         for l in sc.levels:
             l.conv2 = l.conv2[..., :C].contiguous()
@@ -454,7 +457,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, PREC)
+            from banet_b200.host_pipeline import numa_local_to
+            with numa_local_to(dev) as numa:       # this rank's pinned host buffers next to its GPU's PCIe root (matters at N > 1 on a two-socket host)
+                e2e = run_e2e(args, sc, levels, packed, ws, world, local, dev, total_iters, PREC)
+            e2e["host_buffers_numa"] = numa.info
         except Exception as ex:      # e.g. not enough pinnable host memory: report, do not fake
             e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": str(ex)[:200]}
 
@@ -469,12 +475,12 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": workload_name(args), "global_pairs": world * nb, "lm_iterations_per_step": total_iters,
                            "batch_iters_per_s": total_iters / (ms_per_step * 1e-3), "precision": args.precision,
-                           "nvalid_fraction_finest_level": nvalid_frac,
+                           "nvalid_fraction_finest_level": nvalid_frac, "planted_motion": "4 deg / 8 cm" if args.motion == "large" else "1 deg / 2 cm",
                            "conv2_layout": "[F2|gx|gy] (3C channels, the reference's BundleIteration boundary)" if args.layout == "concat"
                                            else "F2 only (C channels); the kernel recomputes gx, gy on the fly (reference grad_fixed, bundlenet.py:92-100)",
                            "l2": "inputs (~33 GB/GPU) far exceed the 126 MB L2; no flush needed",
                            "parallelism": f"pairs sharded over {world} GPU(s), one all-gather of (R,T,W) per step"},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 5), "precision_check": precision_check,
+                "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps * (1 + total_iters * 3), "precision_check": precision_check,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     if world > 1:
