@@ -450,7 +450,7 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         if (cur_b >= 0) dump_rb();
     } else if (warp < W0 + GW + AW) {
         // ===================================================================== algebra warps: 2x7 algebra, R rows, MMA + TMA issue
-        setmaxnreg_dec<64>();
+        setmaxnreg_dec<72>();
         const int awi = warp - (W0 + GW);                    // 0..3: pixels / rows 16*awi .. 16*awi+15
         const int atid = tid - (W0 + GW) * 32;
         const int nlr = awi * 16 + r16;
@@ -620,9 +620,13 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
         }
     } else {
         // ===================================================================== drainer warps: TMEM -> partial slots, fully asynchronous
-        setmaxnreg_dec<40>();
+        setmaxnreg_dec<32>();
         const int dq = warp - (W0 + GW + AW);                // TMEM lane quadrant (= warp % 4)
         const SlotLayout L{KR, C};
+        // The CTA's partial slot (<= 2 x 68 KB) is read-modify-written once per chain of CHAIN tiles.  Left to the default policy the streaming
+        // inputs push it out of L2 between two chains: ncu showed 1.3 GB of DRAM writes per launch (and as many reads) for a kernel that writes
+        // 20 MB of results.  evict-last keeps the 20 MB of slots of all CTAs resident.
+        const uint64_t pol_slot = l2_policy_evict_last();
         auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
             const int row = dq * 32 + lane;
             if (KBLK != 4 && dq * 32 >= KR) return;          // this lane quadrant holds no basis row (warp-uniform)
@@ -634,19 +638,25 @@ lm_build_tc6_kernel(const __grid_constant__ CUtensorMap tmapB, const BuildParams
                 float* dst = slot + (size_t)(cb * 16) * KR + row;
                 if (overwrite) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = v[j];
+                    for (int j = 0; j < 16; ++j) st_f32_hint(dst + (size_t)j * KR, v[j], pol_slot);
                 } else {
-                    float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)j * KR];
+                    for (int hb = 0; hb < 16; hb += 8) {     // 8 columns at a time: the drainers live on 32 registers
+                        float o[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = o[j] + v[j];
+                        for (int j = 0; j < 8; ++j) o[j] = ld_f32_hint(dst + (size_t)(hb + j) * KR, pol_slot);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) st_f32_hint(dst + (size_t)(hb + j) * KR, o[j] + v[hb + j], pol_slot);
+                    }
                 }
             }
             tmem_ld_32x16(tq + KR, v);
             float* dst = slot + L.off_ext() + row;
 #pragma unroll
-            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KR] = v[r]; else dst[r * KR] += v[r]; }
+            for (int r = 0; r < 7; ++r) {
+                if (overwrite) st_f32_hint(dst + r * KR, v[r], pol_slot);
+                else st_f32_hint(dst + r * KR, ld_f32_hint(dst + r * KR, pol_slot) + v[r], pol_slot);
+            }
         };
         int chain = -1, tic = 0, span = 0, cur_b = -1;
         bool first = true;

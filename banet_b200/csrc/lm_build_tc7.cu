@@ -703,6 +703,7 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
         setmaxnreg_dec<40>();
         const int dq = warp - (W0 + GW + AW);                // TMEM lane quadrant (= warp % 4)
         const SlotLayout L{KR, C};
+        const uint64_t pol_slot = l2_policy_evict_last();    // keep the CTA's partial slot L2-resident between two chains (see lm_build_tc6.cu)
         auto drain_region = [&](float* slot, uint32_t col0, bool overwrite) {
             const int row = dq * 32 + lane;
             if (KBLK != 4 && dq * 32 >= KR) return;          // this lane quadrant holds no basis row (warp-uniform)
@@ -714,19 +715,25 @@ lm_build_tc7_kernel(const __grid_constant__ CUtensorMap tmapB, const __grid_cons
                 float* dst = slot + (size_t)(cb * 16) * KR + row;
                 if (overwrite) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = v[j];
+                    for (int j = 0; j < 16; ++j) st_f32_hint(dst + (size_t)j * KR, v[j], pol_slot);
                 } else {
-                    float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = dst[(size_t)j * KR];
+                    for (int hb = 0; hb < 16; hb += 8) {
+                        float o[8];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[(size_t)j * KR] = o[j] + v[j];
+                        for (int j = 0; j < 8; ++j) o[j] = ld_f32_hint(dst + (size_t)(hb + j) * KR, pol_slot);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) st_f32_hint(dst + (size_t)(hb + j) * KR, o[j] + v[hb + j], pol_slot);
+                    }
                 }
             }
             tmem_ld_32x16(tq + KR, v);
             float* dst = slot + L.off_ext() + row;
 #pragma unroll
-            for (int r = 0; r < 7; ++r) { if (overwrite) dst[r * KR] = v[r]; else dst[r * KR] += v[r]; }
+            for (int r = 0; r < 7; ++r) {
+                if (overwrite) st_f32_hint(dst + r * KR, v[r], pol_slot);
+                else st_f32_hint(dst + r * KR, ld_f32_hint(dst + r * KR, pol_slot) + v[r], pol_slot);
+            }
         };
         int chain = -1, tic = 0, span = 0, cur_b = -1;
         bool first = true;

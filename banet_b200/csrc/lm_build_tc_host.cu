@@ -50,13 +50,14 @@ bool tc_supported(const banet_level_t* lv)
            (long long)lv->h * lv->w * lv->conv2_channels < (1LL << 31);
 }
 
-// Generation 7 applies to the F2-only layout on a dense grid (tap coordinates are packed in 16 bits).  It is selected explicitly
-// (banet_set_tuning: tc_generation = 7): measured on B200 (profiles/r02b_*) it moves the fewest bytes and executes 25 % fewer instructions than
-// generation 6, but at 6.0 ms per 640x480 x 32-pair launch it does not beat generation 6 on the same layout (5.9 ms), and its per-tile
-// global-tap fallback is slower under strong local zoom -- so generation 6 stays the default everywhere.
+// Generation 7 applies to the F2-only layout on a dense grid (tap coordinates are packed in 16 bits).  Default choice (tc_generation = 0),
+// from interleaved A/B runs at the board's steady power state (profiles/r02d_gen6_vs_gen7_f2layout.txt): in the single-pass mode (TF32X1)
+// generation 7 is 9 % (640x480) to 15 % (320x240) faster than generation 6 on this layout; in the two- and three-pass modes its gather
+// warps also carry the operand splitting and generation 6 is faster.  banet_set_tuning forces either (6 / 7).
 static bool use_gen7(const banet_level_t* lv, int mode, int kblk)
 {
-    return g_tuning.tc_generation == 7 && lv->conv2_channels == lv->C && lv->grid_w > 0 && lv->h < 65536 && lv->w < 65536 &&
+    const bool wanted = g_tuning.tc_generation == 7 || (g_tuning.tc_generation == 0 && mode == 1);
+    return wanted && lv->conv2_channels == lv->C && lv->grid_w > 0 && lv->h < 65536 && lv->w < 65536 &&
            lm_build_tc7_supported(mode, lv->C / 64, kblk);
 }
 

@@ -86,6 +86,12 @@ __device__ __forceinline__ float4 ld_stream_f4_hint(const float* p, uint64_t pol
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
     return r;
 }
+__device__ __forceinline__ float ld_f32_hint(const float* p, uint64_t pol) {
+    float r; asm volatile("ld.global.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol) : "memory"); return r;
+}
+__device__ __forceinline__ void st_f32_hint(float* p, float v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" :: "l"(p), "f"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ float4 ldg4_hint(const float* p, uint64_t pol) {
     float4 r;
     asm("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));

@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--layout", default="concat", choices=["concat", "f2"],
                     help="conv2 in HBM: 'concat' = [F2|gx|gy] (3C, the reference's BundleIteration boundary), 'f2' = F2 only, gradients on the fly")
     ap.add_argument("--no-precision-check", action="store_true")
+    ap.add_argument("--tc-generation", type=int, default=0, choices=[0, 6, 7], help="diagnostic: banet_set_tuning(tc_generation) (0 = library default)")
     ap.add_argument("--motion", default="default", choices=["default", "large"],
                     help="planted relative motion of the synthetic pairs: default 1 deg / 2 cm (SURVEY.md section 8d), large 4 deg / 8 cm (less tap locality, fewer in-bounds points)")
     ap.add_argument("--e2e-boundary", default="resize", choices=["resize", "features", "concat"],
@@ -345,6 +346,8 @@ def main():
         td.init_process_group("nccl", device_id=dev)
 
     C, K, nb, iters = args.channels, args.bases, args.nb, args.iters
+    if args.tc_generation:
+        _lib.set_tuning(tc_generation=args.tc_generation)
     motion = dict(rot_deg=4.0, trans_m=0.08, start_trans_noise_m=0.02) if args.motion == "large" else {}
     sc = synth.make_scene(nb=nb, H=H_FULL, W=W_FULL, C=C, K=K, level_ids=LEVEL_IDS, seed=1234 + 2 + 1000 * rank,
                           device=dev, dtype=torch.float32, **motion)

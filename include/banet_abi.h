@@ -44,7 +44,7 @@ int         banet_num_sms(void);
 /* Diagnostic / test knobs (process-wide; defaults = production).  Results never depend on them beyond
  * fp32 summation order. */
 typedef struct banet_tuning {
-    int tc_generation;      /* 0 or 6: generation 6 (ld.global taps; the default: fastest measured); 7: TMA-staged F2 windows where they apply (F2-only layout + dense grid) */
+    int tc_generation;      /* 0: default (generation 7 = TMA-staged F2 windows for F2-only layout + dense grid + single-pass TF32X1, generation 6 = ld.global taps otherwise); 6 / 7: force one wherever it applies */
     int tc7_force_direct;   /* 1: generation 7 takes its per-tile global-tap fallback for every tile (tests the fallback) */
     int tc7_band_rows;      /* generation 7 walks the 8x8 tiles of a pair in bands of this many tile rows (L2 reuse of the window halos); default 4 */
     int tc6_band_rows;      /* generation 6, dense grid: same walk (tap rows shared by vertically adjacent tiles are re-read from L2, not HBM); 0 = default, 1 = row-major */

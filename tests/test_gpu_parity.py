@@ -283,14 +283,15 @@ def test_full_size_properties():
     assert e1 < 0.05 * e0 and (W - sc.W_true).norm().item() < 0.2 * sc.W_true.norm().item()
 
 
-def test_cfg1_reference_cpu_case():
+@pytest.mark.parametrize("C", [128, 32])
+def test_cfg1_reference_cpu_case(C):
     """BASELINE.json configs[0] — the reference's own CPU-runnable case: one 2-frame pair, 160x120 single scale, K=16 depth
-    bases, 3 LM iterations with the lambda-MLP (C=32 to keep the float64 oracle's materialised J quick) — whole solve against
-    the oracle at the north-star tolerance, through banet_lm_run and through the mirror class."""
+    bases, 3 LM iterations with the lambda-MLP, at the pyramid width of the headline configs (C=128) and at C=32 — whole solve against
+    the oracle's reference-faithful materialised form at the north-star tolerance, through banet_lm_run."""
     ops = _ops()
-    sc = scene_case(nb=1, H=120, W=160, C=32, K=16, level_ids=(3,), seed=1235, dtype=torch.float32)
+    sc = scene_case(nb=1, H=120, W=160, C=C, K=16, level_ids=(3,), seed=1235, dtype=torch.float32)
     lv = sc.levels[0]
-    mlp = mlp_for(32, 3)
+    mlp = mlp_for(C, 3)
     a = oracle_level_inputs(lv)
     ol = O.LevelInputs(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"], mlp)
     oR, oT, oW = O.lm_solve([ol], 3, sc.R0.double(), sc.T0.double(), sc.W0.double(), O.IterOptions(l2_regularizer_base=1000.0))
