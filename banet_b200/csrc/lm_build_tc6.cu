@@ -1,14 +1,15 @@
 // lm_build_tc6.cu — tensor-core build kernel, generation 6: every phase has its own warpgroup, phases of different tiles overlap.
 //
-// Same contract, slot layout and precision modes as lm_build_tc.cu (read its header first).  Roles (896 threads, 1 CTA / SM):
+// Contract, slot layout and precision modes: see lm_build_tc_host.cu.  Roles (896 threads, 1 CTA / SM; register budgets by setmaxnreg,
+// 48 / 88 / 72 / 32 = 64 512 of the SM's 65 536 registers):
 //
 //   warpgroup 0    4 geometry warps, 16 pixels each per tile, run ahead of everybody:                              (48 regs)
 //                    b.W from the TMA-staged basis tile, warp / mask / tap offsets -> pixel records (ring of NREC)
 //   warpgroups 1-4 16 gather warps, 4 pixels each per tile: records -> 13 tap loads -> blend / accumulate -> M, q  (88 regs)
-//   warpgroup 5    4 algebra warps, 16 pixels each per tile:                                                        (64 regs)
+//   warpgroup 5    4 algebra warps, 16 pixels each per tile:                                                        (72 regs)
 //                    2x7 per-pixel algebra (H_cc / g_c partials in registers), R rows (A_lo, R_lo) into smem,
 //                    then ONE elected thread issues the tile's tcgen05.mma and refills the freed basis stage by TMA
-//   warpgroup 6    4 drainer warps (one TMEM lane quadrant each): TMEM chains -> partial slots, fully asynchronous  (40 regs)
+//   warpgroup 6    4 drainer warps (one TMEM lane quadrant each): TMEM chains -> partial slots (L2 evict-last), asynchronous (32 regs)
 //   mbarriers: fullB[NST] TMA landed | recs[NREC] geometry->gather | gath[NREC] gather->algebra | recfree[NREC] algebra->geometry |
 //              rfree MMAs of the tile done (R, A_lo and the A stage reusable) | chain_done/drained[2], flushb, tmemfree issuer<->drainers |
 //              rbdump/rbfree gather<->algebra hand-over of the |diff| sums at a pair change.

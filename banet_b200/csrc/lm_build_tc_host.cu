@@ -20,7 +20,7 @@
 // Kernel generations:
 //   7 (lm_build_tc7.cu)  F2-only conv2 + dense grid: the tile's F2 footprint is staged into shared memory by TMA (channel chunks),
 //                        the 12 gradient/bilinear taps of every pixel come from LDS; per-tile fallback to global taps when the
-//                        footprint of a tile does not fit the staged window.  MODE 1 and 2.
+//                        footprint of a tile does not fit the staged window.  MODE 1 (where it is the default) and 2.
 //   6 (lm_build_tc6.cu)  everything else (the reference's [F2|gx|gy] layout, unstructured point lists, MODE 3): taps by ld.global.
 #include "common.cuh"
 #include "lm_build.h"
