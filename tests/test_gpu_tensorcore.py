@@ -185,3 +185,27 @@ def test_cfg4_window_sparse_points_solve():
         if prec in (0, 3):
             for e, f in zip(errs, floor):
                 assert e < max(1e-4, 2.0 * f)
+
+
+@pytest.mark.parametrize("K", [64, 32])
+def test_small_basis_counts_on_the_tensor_cores(K):
+    """K = 64 / 32 (BASELINE.json configs[4], the K sweep): the generation-6 kernel with KBLK = K / 32 basis blocks against the float64
+    oracle, with and without the dense-grid hint, in the two- and three-pass modes (the single-pass mode is instantiated for K = 128 only, so
+    AUTO resolves to TF32X2 here) and against the FP32 SIMT path.  First measured in round 2 (profiles/r02a_small_k_check.txt: relH 1.0e-7 /
+    2.6e-8 / 2.4e-8 for X2 / X3 / FP32)."""
+    from banet_b200 import ops, synth, _lib
+    sc = synth.make_scene(nb=3, H=96, W=128, C=64, K=K, level_ids=(3,), seed=50 + K, device="cpu", dtype=torch.float32)
+    lv = sc.levels[0]
+    a = oracle_level_inputs(lv)
+    Wt = sc.W0 + 0.01 * torch.randn(sc.W0.shape, generator=torch.Generator().manual_seed(1))
+    rH, rg, _, rnv = O.normal_equations_structured(a["conv1"], a["conv2"], a["fx"], a["fy"], a["ox"], a["oy"], a["p"], a["D"], a["B"],
+                                                   sc.R0.double(), sc.T0.double(), Wt.double())
+    cu = lambda t: t.cuda()
+    for grid in (None, lv.grid):
+        L = ops.Level(cu(lv.conv1), cu(lv.conv2), cu(lv.intr), cu(lv.p), cu(lv.D), cu(lv.B), grid=grid)
+        for prec, tol in ((_lib.PREC_FP32_SIMT, 2e-7), (_lib.PREC_TF32X2, 1e-6), (_lib.PREC_TF32X3, 2e-7), (_lib.PREC_AUTO, 1e-6)):
+            H, g, rbar, nv = ops.lm_build(L, cu(sc.R0), cu(sc.T0), cu(Wt), precision=prec)
+            eH, eg = rel_fro(H, rH), rel_fro(g, rg.squeeze(-1))
+            print(f"K={K} grid={grid is not None} prec={prec}: relH {eH:.2e} relg {eg:.2e}")
+            assert eH < tol and eg < tol, (K, grid is not None, prec, eH, eg)
+            assert torch.equal(nv.cpu().double(), rnv)
