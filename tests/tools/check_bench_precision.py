@@ -1,7 +1,7 @@
 """GPU: outputs of the bench workload (cfg2: nb pairs, 4 levels x 5 iterations, lambda-MLP) in every precision mode against the
 FP32 SIMT path (which the parity tests pin to the oracle)."""
 import os, sys, torch
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import bench
 from banet_b200 import ops, synth, _lib
 nb = int(os.environ.get("BANET_NB", "8")); C = K = 128; iters = 5

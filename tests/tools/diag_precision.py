@@ -1,6 +1,6 @@
 """Diagnostic (GPU): where does the output error of one LM iteration come from?  Run under gpurun."""
 import sys, os
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import torch
 from helpers import O, scene_case, oracle_level_inputs, to_cuda32, rel_fro
 from banet_b200 import ops

@@ -1,7 +1,7 @@
 """Round-2 GPU probe 1: (a) whole-solve accuracy of every precision policy against the float64 oracle on a cfg2-shaped case
 (4 levels, C=K=128, lambda-MLP, 5 iterations per level, nb=2; both conv2 layouts); (b) generation 6 vs 7 timing at 640x480, nb=32."""
 import json, os, sys, time, statistics, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from banet_b200 import ops, synth, _lib
 from helpers import O, oracle_level_inputs, rel_fro

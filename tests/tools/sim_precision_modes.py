@@ -3,7 +3,7 @@ scheme does to H, g and the LM step on a bench-like smooth scene: hardware trunc
 stochastic rounding, exact split (TF32X2).  Run: python scripts/sim_precision_modes.py   (no GPU needed; imports the oracle — a
 diagnostic, not part of the product)."""
 import sys, os, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
 from helpers import O, oracle_level_inputs, rel_fro
 from oracle import ba_oracle as BO
 from banet_b200 import synth

@@ -3,7 +3,7 @@ rounding schemes against the exact-split TF32X2 scheme over many LM iterations: 
 iteration), stochastic rounding re-drawn per iteration, and antithetic dither (iteration 2k+1 uses the complement of iteration 2k).
 Run: python scripts/sim_precision_solve.py   (no GPU; a diagnostic that imports the oracle, not part of the product)."""
 import os, sys, torch
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
 from helpers import oracle_level_inputs, rel_fro
 from oracle import ba_oracle as BO
 from banet_b200 import synth
