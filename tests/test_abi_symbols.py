@@ -43,14 +43,18 @@ def test_version_and_error_paths_without_gpu():
 
 
 def test_product_never_touches_the_oracle():
-    """The product path must not import, call or fall back to anything under oracle/."""
-    pkg = os.path.join(ROOT, "banet_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
-                txt = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
-                assert "ba_oracle" not in txt, f"{f} references the oracle"
+    """The product path must not import, call or fall back to anything under oracle/ -- nor may scripts/ or the C headers: only tests/,
+    __graft_entry__.smoke() and bench.py's CPU legs use the checker."""
+    for top in ("banet_b200", "scripts", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh")):
+                    txt = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
+                    assert "ba_oracle" not in txt and "from helpers import" not in txt, f"{f} references the oracle"
+    entry = open(os.path.join(ROOT, "__graft_entry__.py")).read()
+    body = entry[:entry.index("def smoke")]                       # build() may compile the checker; only smoke() may run it
+    assert not re.search(r"^\s*(from|import)\s+oracle\b", body, flags=re.M)
 
 
 def test_cpu_tensors_are_rejected_loudly():
