@@ -36,22 +36,25 @@ class numa_local_to:
     host this keeps every rank's host->device traffic off the inter-socket link.  Restores the previous affinity on exit.  A no-op (with
     `.info` saying why) when the topology cannot be read — it never fails the caller."""
 
-    def __init__(self, device):
+    def __init__(self, device, _bdf: Optional[str] = None, _sysfs: str = "/sys"):
         self.device = torch.device(device)
         self.info = {"node": None, "cpus": None, "note": "not applied"}
         self._saved = None
+        self._bdf, self._sysfs = _bdf, _sysfs                      # test hooks: PCI address and sysfs root
 
     def __enter__(self):
         import os
         try:
-            pr = torch.cuda.get_device_properties(self.device)
-            bdf = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
-            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+            bdf = self._bdf
+            if bdf is None:
+                pr = torch.cuda.get_device_properties(self.device)
+                bdf = "%04x:%02x:%02x.0" % (int(pr.pci_domain_id), int(pr.pci_bus_id), int(pr.pci_device_id))
+            node = int(open(f"{self._sysfs}/bus/pci/devices/{bdf}/numa_node").read().strip())
             if node < 0:
                 self.info["note"] = f"{bdf}: numa_node unknown (-1)"
                 return self
             cpus = set()
-            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            for part in open(f"{self._sysfs}/devices/system/node/node{node}/cpulist").read().strip().split(","):
                 a, _, b = part.partition("-")
                 cpus.update(range(int(a), int(b or a) + 1))
             self._saved = os.sched_getaffinity(0)

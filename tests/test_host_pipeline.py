@@ -77,3 +77,31 @@ def test_resize_host_solver_matches_explicit_derivation(chunks):
     R1, T1, W1, st1 = ops.lm_run(levels, 4, sc.R0, sc.T0, sc.W0, lambda_fixed=0.5, precision=0)
     # a different batch size per call moves the CTA / partial-slot boundaries: same maths, different fp32 summation order
     assert rel_fro(R, R1) < 2e-5 and rel_fro(T, T1) < 1e-3 and rel_fro(W, W1) < 5e-3
+
+
+def test_numa_binding_follows_sysfs_and_restores_the_affinity(tmp_path):
+    """host_pipeline.numa_local_to: the calling thread runs on the CPUs of the GPU's NUMA node while host buffers are allocated, and gets its
+    affinity back afterwards; anything unreadable makes it a no-op.  (A fake sysfs tree: no GPU needed.)"""
+    import os
+    from banet_b200.host_pipeline import numa_local_to
+    before = os.sched_getaffinity(0)
+    cpus = sorted(before)
+    node_cpus = cpus[: max(1, len(cpus) // 2)]
+    bdf = "0000:1b:00.0"
+    (tmp_path / "bus/pci/devices" / bdf).mkdir(parents=True)
+    (tmp_path / "bus/pci/devices" / bdf / "numa_node").write_text("1\n")
+    (tmp_path / "devices/system/node/node1").mkdir(parents=True)
+    lo, hi = node_cpus[0], node_cpus[-1]
+    listed = [c for c in range(lo, hi + 1)]                                  # a range like the kernel prints it, plus a CPU we may not own
+    (tmp_path / "devices/system/node/node1/cpulist").write_text(f"{lo}-{hi},{max(cpus) + 1000}\n")
+    with numa_local_to("cuda:0", _bdf=bdf, _sysfs=str(tmp_path)) as n:
+        inside = os.sched_getaffinity(0)
+    assert inside == set(listed) & before and n.info["node"] == 1 and n.info["cpus"] == len(inside)
+    assert os.sched_getaffinity(0) == before
+    (tmp_path / "bus/pci/devices" / bdf / "numa_node").write_text("-1\n")          # unknown node: nothing changes
+    with numa_local_to("cuda:0", _bdf=bdf, _sysfs=str(tmp_path)) as n:
+        assert os.sched_getaffinity(0) == before
+    assert n.info["node"] is None and os.sched_getaffinity(0) == before
+    with numa_local_to("cuda:0", _bdf="ffff:ff:1f.0", _sysfs=str(tmp_path)) as n:   # unreadable topology: a no-op, never an exception
+        assert os.sched_getaffinity(0) == before
+    assert "unavailable" in n.info["note"]
